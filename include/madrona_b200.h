@@ -1,0 +1,144 @@
+/* madrona_b200.h -- C ABI of libmadrona_b200.so, the B200-native drop-in for
+ * the Madrona GPU backend (madrona::MWCudaExecutor).
+ *
+ * Every entry point cites the reference interface it replaces
+ * (/root/reference = shacklettbp/madrona @ b31034bd).  Only plain C types
+ * cross this boundary: no torch, no C++ classes.  The C++ facade with the
+ * reference's exact class names (madrona::MWCudaExecutor, MWCudaLaunchGraph,
+ * StateConfig, CompileConfig) is the header-only wrapper in
+ * madrona_b200/host/madrona/mw_gpu.hpp; Python binds the same symbols with
+ * ctypes (madrona_b200/executor.py).
+ *
+ * Error convention: the reference FATAL()s (print + abort,
+ * include/madrona/crash.hpp).  The C ABI instead returns NULL / non-zero and
+ * keeps a message retrievable with mb2_last_error(); the C++ facade turns
+ * that back into print + abort so C++ callers see reference behaviour.
+ */
+#ifndef MADRONA_B200_H
+#define MADRONA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb2_executor mb2_executor;
+typedef struct mb2_launch_graph mb2_launch_graph;
+
+/* == madrona::StateConfig, include/madrona/mw_gpu.hpp:25-51 (same fields,
+ * same order, same meaning; host pointers are copied during create). */
+typedef struct mb2_state_config {
+    const void *world_init_ptr;
+    uint32_t num_world_init_bytes;
+    const void *user_config_ptr;
+    uint32_t num_user_config_bytes;
+    uint32_t num_world_data_bytes;
+    uint32_t world_data_alignment;
+    uint32_t num_worlds;
+    uint32_t num_taskgraphs;
+    uint32_t num_exported_buffers;
+} mb2_state_config;
+
+/* == madrona::CompileConfig, include/madrona/mw_gpu.hpp:53-73.  user_sources
+ * are the simulator's C++ files (the same files the reference NVRTC-compiles);
+ * opt_mode: 0 Optimize, 1 LTO (treated as Optimize: single-module build),
+ * 2 Debug. */
+typedef struct mb2_compile_config {
+    const char *const *user_sources;
+    uint32_t num_user_sources;
+    const char *const *user_compile_flags;
+    uint32_t num_user_compile_flags;
+    uint32_t opt_mode;
+} mb2_compile_config;
+
+/* == madrona::CudaBatchRenderConfig, include/madrona/mw_gpu.hpp:75-96, with
+ * render::MeshBVHData flattened to plain device/host arrays
+ * (include/madrona/render/cuda_batch_render_assets.hpp). */
+typedef struct mb2_render_config {
+    uint32_t render_mode;          /* 0 RGBD, 1 Depth */
+    uint32_t render_resolution;    /* square output */
+    float near_plane;
+    float far_plane;
+    const void *mesh_bvhs;         /* host array of mb2 mesh descriptors */
+    uint32_t num_mesh_bvhs;
+    const void *vertices;          /* host float[3*num_vertices] */
+    uint32_t num_vertices;
+    const void *indices;           /* host uint32[3*num_triangles] */
+    uint32_t num_triangles;
+} mb2_render_config;
+
+/* MWCudaExecutor::initCUDA(int gpu_id), mw_gpu.hpp:122 / cuda_exec.cpp:2315.
+ * Returns 0 on success. */
+int mb2_init_cuda(int gpu_id);
+
+/* MWCudaExecutor::MWCudaExecutor(const StateConfig&, const CompileConfig&,
+ * CUcontext, const Optional<CudaBatchRenderConfig>&), mw_gpu.hpp:125-129 /
+ * cuda_exec.cpp:2333-2420.  render_cfg may be NULL. */
+mb2_executor *mb2_executor_create(const mb2_state_config *state_cfg,
+                                  const mb2_compile_config *compile_cfg,
+                                  int gpu_id,
+                                  const mb2_render_config *render_cfg);
+
+/* ~MWCudaExecutor(), mw_gpu.hpp:132. */
+void mb2_executor_destroy(mb2_executor *exec);
+
+/* MWCudaExecutor::buildLaunchGraph(Span<const uint32_t>, const char*),
+ * mw_gpu.hpp:144-145 / cuda_exec.cpp:2174-2291. */
+mb2_launch_graph *mb2_build_launch_graph(mb2_executor *exec,
+                                         const uint32_t *taskgraph_ids,
+                                         uint32_t num_taskgraphs,
+                                         const char *stat_name);
+
+/* MWCudaExecutor::buildLaunchGraphAllTaskGraphs(), mw_gpu.hpp:147. */
+mb2_launch_graph *mb2_build_launch_graph_all(mb2_executor *exec);
+
+/* MWCudaExecutor::buildRenderGraph(), mw_gpu.hpp:150 / cuda_exec.cpp:2527. */
+mb2_launch_graph *mb2_build_render_graph(mb2_executor *exec);
+
+/* ~MWCudaLaunchGraph(), mw_gpu.hpp:104. */
+void mb2_launch_graph_destroy(mb2_launch_graph *graph);
+
+/* MWCudaExecutor::run(MWCudaLaunchGraph&), mw_gpu.hpp:153 /
+ * cuda_exec.cpp:2756-2794: launch + synchronise.  Returns 0 on success. */
+int mb2_run(mb2_executor *exec, mb2_launch_graph *graph);
+
+/* MWCudaExecutor::runAsync(MWCudaLaunchGraph&, cudaStream_t), mw_gpu.hpp:155
+ * / cuda_exec.cpp:2796-2800: enqueue only; cuda_stream is a cudaStream_t. */
+int mb2_run_async(mb2_executor *exec, mb2_launch_graph *graph,
+                  void *cuda_stream);
+
+/* MWCudaExecutor::getExported(CountT slot), mw_gpu.hpp:159: borrowed device
+ * pointer, stable for the executor's lifetime. */
+void *mb2_get_exported(const mb2_executor *exec, int64_t slot);
+
+/* ---- additions with no reference counterpart (introspection) ------------ */
+
+/* Message of the last failed call on this thread ("" if none). */
+const char *mb2_last_error(void);
+
+/* Live row count of the table behind an export slot (device sync + read). */
+int64_t mb2_get_exported_num_rows(mb2_executor *exec, int64_t slot);
+
+/* Bytes per row of the exported component. */
+int64_t mb2_get_exported_row_bytes(const mb2_executor *exec, int64_t slot);
+
+/* Kernel nodes inside a built launch graph (== launches per run). */
+int64_t mb2_launch_graph_num_kernels(const mb2_launch_graph *graph);
+
+/* The stream mb2_run launches on (cudaStream_t). */
+void *mb2_executor_stream(mb2_executor *exec);
+
+/* Compile the simulator module for sm_100a without touching a GPU and store
+ * it in the kernel cache (used by the build step on a CPU-only box).
+ * Returns 0 on success. */
+int mb2_jit_precompile(const mb2_compile_config *compile_cfg);
+
+/* Version string. */
+const char *mb2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

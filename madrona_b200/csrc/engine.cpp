@@ -1,0 +1,704 @@
+// engine.cpp -- libmadrona_b200.so host side: the C ABI declared in
+// include/madrona_b200.h.  Replaces the reference's MWCudaExecutor
+// implementation (src/mw/cuda_exec.cpp, 2807 LoC: NVRTC+nvJitLink megakernel
+// build, VM allocator thread, print thread, megakernel CUDA graph) with:
+//   JIT (jit.cpp) -> load cubin -> device-side registerTypes -> host allocates
+//   SoA tables -> two-pass deterministic world construction -> device-side
+//   setupTasks -> one CUDA graph per launch graph with one kernel node per
+//   TaskGraph node (stream capture).
+// The product path is CUDA only: there is no CPU fallback anywhere in here.
+#include "../../include/madrona_b200.h"
+#include "engine.hpp"
+#include "physics_host.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+namespace mb2 {
+
+static thread_local std::string g_last_error;
+
+void setError(const std::string &msg)
+{
+    g_last_error = msg;
+    if (getenv("MADRONA_B200_VERBOSE")) fprintf(stderr, "[madrona_b200] %s\n", msg.c_str());
+}
+
+#define MB2_CUDA(expr) do { \
+    cudaError_t mb2_err_ = (expr); \
+    if (mb2_err_ != cudaSuccess) { \
+        setError(std::string(#expr) + ": " + cudaGetErrorString(mb2_err_)); \
+        return false; \
+    } } while (0)
+
+static bool devAlloc(Executor *ex, void **ptr, size_t bytes, bool zero = true)
+{
+    if (bytes == 0) bytes = 16;
+    MB2_CUDA(cudaMalloc(ptr, bytes));
+    ex->allocations.push_back(*ptr);
+    if (zero) MB2_CUDA(cudaMemsetAsync(*ptr, 0, bytes, ex->stream));
+    return true;
+}
+
+static bool pushState(Executor *ex)
+{
+    MB2_CUDA(cudaMemcpyAsync(ex->dState, ex->hState, sizeof(EngineState),
+                             cudaMemcpyHostToDevice, ex->stream));
+    MB2_CUDA(cudaStreamSynchronize(ex->stream));
+    return true;
+}
+
+static bool pullState(Executor *ex)
+{
+    MB2_CUDA(cudaStreamSynchronize(ex->stream));
+    MB2_CUDA(cudaMemcpy(ex->hState, ex->dState, sizeof(EngineState),
+                        cudaMemcpyDeviceToHost));
+    return true;
+}
+
+static std::string describeErrors(uint32_t flags, uint32_t archetype)
+{
+    std::string s;
+    if (flags & ErrTableOverflow) s += "table overflow (archetype " + std::to_string(archetype) +
+        "; raise MADRONA_B200_ROWS_PER_WORLD) ";
+    if (flags & ErrEntityOverflow) s += "entity store overflow ";
+    if (flags & ErrTmpOverflow) s += "tmp allocator overflow (raise MADRONA_B200_TMP_BYTES) ";
+    if (flags & ErrPersistOverflow) s += "persistent arena overflow (raise MADRONA_B200_PERSIST_BYTES) ";
+    if (flags & ErrTooManyNodes) s += "too many taskgraph nodes ";
+    if (flags & ErrRegistry) s += "ECS registration error (unregistered component, too many types, bad export slot) ";
+    if (flags & ErrPhysicsOverflow) s += "physics buffer overflow ";
+    return s;
+}
+
+static bool checkDeviceErrors(Executor *ex, const char *phase)
+{
+    uint32_t st[2];
+    MB2_CUDA(cudaMemcpy(st, &ex->dState->errorFlags, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[0] != 0) {
+        setError(std::string(phase) + ": " + describeErrors(st[0], st[1]));
+        return false;
+    }
+    return true;
+}
+
+static bool launch1(Executor *ex, cudaKernel_t k, unsigned grid, unsigned block)
+{
+    void *args[1] = { nullptr };
+    MB2_CUDA(cudaLaunchKernel((const void *)k, dim3(grid), dim3(block), args, 0, ex->stream));
+    MB2_CUDA(cudaStreamSynchronize(ex->stream));
+    return true;
+}
+
+static uint64_t envU64(const char *name, uint64_t dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return strtoull(v, nullptr, 10);
+}
+
+// ---- table allocation after registerTypes ---------------------------------
+
+static bool allocateTables(Executor *ex)
+{
+    EngineState &S = *ex->hState;
+    const uint32_t W = S.numWorlds;
+
+    memset(S.columnLookup, 0xff, sizeof(S.columnLookup));
+
+    uint64_t total_entity_rows = 0;
+    for (uint32_t a = 0; a < S.numArchetypes; a++) {
+        const ArchetypeInfo &info = S.archetypes[a];
+        TableDesc &t = S.tables[a];
+        memset(&t, 0, sizeof(t));
+        if (!info.registered) continue;
+
+        uint64_t cap;
+        if (info.isSingleton) cap = W;
+        else if (info.maxPerWorld > 0) cap = (uint64_t)W * (uint64_t)info.maxPerWorld;
+        else cap = (uint64_t)W * ex->rowsPerWorldHint;
+        if (cap > 0x7fffff00ull) {
+            setError("table too large");
+            return false;
+        }
+        cap = (cap + 255) & ~255ull;
+
+        t.numColumns = (int32_t)info.numUserComponents + 2;
+        t.capacity = (int32_t)cap;
+        t.maxPerWorld = info.maxPerWorld;
+        t.isSingleton = info.isSingleton;
+        t.numRows = info.isSingleton ? (int32_t)W : 0;
+
+        for (int32_t c = 0; c < t.numColumns; c++) {
+            uint32_t cid = c == 0 ? 0u : (c == 1 ? 1u : info.componentIDs[c - 2]);
+            if (cid >= S.numComponents) {
+                setError("archetype " + std::to_string(a) + " uses an unregistered component");
+                return false;
+            }
+            uint32_t bytes = S.components[cid].numBytes;
+            t.columnBytes[c] = bytes;
+            if (!devAlloc(ex, &t.columns[c], (size_t)bytes * cap + 256)) return false;
+            S.columnLookup[a][cid] = (i16)c;
+        }
+        if (!devAlloc(ex, (void **)&t.worldOffsets, sizeof(int32_t) * W)) return false;
+        if (!devAlloc(ex, (void **)&t.worldCounts, sizeof(int32_t) * W)) return false;
+        if (!info.isSingleton) total_entity_rows += cap;
+    }
+
+    // exports: pointer == base of the live column (reference:
+    // src/mw/device/include/madrona/state.inl:522-532)
+    for (uint32_t s = 0; s < S.numExported && s < (uint32_t)kMaxExports; s++) {
+        const ExportInfo &e = S.exports[s];
+        if (!e.used) continue;
+        if (e.archetype >= S.numArchetypes || e.component >= S.numComponents ||
+                S.columnLookup[e.archetype][e.component] < 0) {
+            setError("export slot " + std::to_string(s) + " names a component its archetype lacks");
+            return false;
+        }
+        int col = S.columnLookup[e.archetype][e.component];
+        ex->exported[s] = S.tables[e.archetype].columns[col];
+        ex->exportArchetype[s] = e.archetype;
+        ex->exportRowBytes[s] = S.tables[e.archetype].columnBytes[col];
+    }
+
+    // entity store: singleton rows take the first IDs in registration order,
+    // exactly as the CPU backend's init_state_cache_ hands them out
+    // (include/madrona/state.inl:163-179).
+    uint64_t singleton_ids = (uint64_t)S.numSingletons * W;
+    uint64_t init_blocks = (singleton_ids + kIDsPerCache - 1) / kIDsPerCache;
+    uint64_t ent_cap = init_blocks * kIDsPerCache + total_entity_rows +
+        (uint64_t)W * kIDsPerCache * 2;
+    ent_cap = (ent_cap + kIDsPerCache - 1) / kIDsPerCache * kIDsPerCache;
+    if (ent_cap > 0x7fffff00ull) {
+        setError("entity store too large");
+        return false;
+    }
+    S.entityCapacity = (int32_t)ent_cap;
+    S.initExpandBlocks = (int32_t)init_blocks;
+    S.numEntitySlots = (int32_t)(init_blocks * kIDsPerCache);
+    S.freeHead = ((u64)0 << 32) | (u32)kIDSentinel;
+    if (!devAlloc(ex, (void **)&S.entitySlots, sizeof(EntitySlot) * ent_cap)) return false;
+    if (!devAlloc(ex, (void **)&S.idCaches, sizeof(IDCache) * W)) return false;
+
+    S.tmpCapacity = envU64("MADRONA_B200_TMP_BYTES", 256ull << 20);
+    S.persistCapacity = envU64("MADRONA_B200_PERSIST_BYTES", (64ull << 20) + (uint64_t)W * (24ull << 10));
+    if (!devAlloc(ex, (void **)&S.tmpArena, S.tmpCapacity, false)) return false;
+    if (!devAlloc(ex, (void **)&S.persistArena, S.persistCapacity)) return false;
+    S.tmpOffset = 0;
+    S.persistOffset = 0;
+    return true;
+}
+
+static bool resetForInitPass(Executor *ex, uint32_t pass, const std::vector<int32_t> &expand_base,
+                             uint64_t persist_mark)
+{
+    EngineState &S = *ex->hState;
+    const uint32_t W = S.numWorlds;
+    for (uint32_t a = 0; a < S.numArchetypes; a++) {
+        TableDesc &t = S.tables[a];
+        if (!S.archetypes[a].registered) continue;
+        if (t.isSingleton) {
+            t.numRows = (int32_t)W;
+            for (int32_t c = 2; c < t.numColumns; c++) {
+                MB2_CUDA(cudaMemsetAsync(t.columns[c], 0, (size_t)t.columnBytes[c] * t.capacity, ex->stream));
+            }
+        } else {
+            t.numRows = 0;
+        }
+        t.needsSort = 0;
+        t.highWater = 0;
+    }
+    MB2_CUDA(cudaMemsetAsync(S.entitySlots, 0, sizeof(EntitySlot) * (size_t)S.entityCapacity, ex->stream));
+    std::vector<IDCache> caches(W);
+    for (uint32_t w = 0; w < W; w++) {
+        IDCache &c = caches[w];
+        memset(&c, 0, sizeof(c));
+        c.freeHead = kIDSentinel;
+        c.overflowHead = kIDSentinel;
+        c.expandBase = expand_base.empty() ? 0 : expand_base[w];
+    }
+    MB2_CUDA(cudaMemcpyAsync(S.idCaches, caches.data(), sizeof(IDCache) * W,
+                             cudaMemcpyHostToDevice, ex->stream));
+    MB2_CUDA(cudaMemsetAsync(S.worldData, 0, (size_t)S.worldDataStride * W, ex->stream));
+    S.numEntitySlots = S.initExpandBlocks * kIDsPerCache;
+    S.freeHead = ((u64)0 << 32) | (u32)kIDSentinel;
+    S.tmpOffset = 0;
+    S.persistOffset = persist_mark;
+    S.errorFlags = 0;
+    S.initPass = pass;
+    if (!pushState(ex)) return false;
+    launchFillSingletons(ex, ex->stream);
+    MB2_CUDA(cudaStreamSynchronize(ex->stream));
+    return true;
+}
+
+static bool createExecutor(Executor *ex, const mb2_state_config *sc,
+                           const mb2_compile_config *cc,
+                           const mb2_render_config *rc)
+{
+    if (sc->num_worlds == 0) {
+        setError("numWorlds must be > 0");
+        return false;
+    }
+    if (sc->num_taskgraphs > (uint32_t)kMaxTaskGraphs) {
+        setError("too many taskgraphs");
+        return false;
+    }
+    if (sc->num_exported_buffers > (uint32_t)kMaxExports) {
+        setError("too many exported buffers");
+        return false;
+    }
+
+    MB2_CUDA(cudaSetDevice(ex->gpu));
+    cudaDeviceProp prop;
+    MB2_CUDA(cudaGetDeviceProperties(&prop, ex->gpu));
+    ex->numSMs = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        setError("madrona_b200 requires an sm_100a device (found sm_" +
+                 std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+        return false;
+    }
+    MB2_CUDA(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
+    ex->rowsPerWorldHint = envU64("MADRONA_B200_ROWS_PER_WORLD", 64);
+
+    // ---- JIT the simulator
+    std::vector<std::string> sources, flags;
+    for (uint32_t i = 0; i < cc->num_user_sources; i++) sources.push_back(cc->user_sources[i]);
+    for (uint32_t i = 0; i < cc->num_user_compile_flags; i++) flags.push_back(cc->user_compile_flags[i]);
+    std::string err;
+    if (!jitCompile(sources, flags, (int)cc->opt_mode, &ex->jit, &err)) {
+        setError(err);
+        return false;
+    }
+    MB2_CUDA(cudaLibraryLoadData(&ex->lib, ex->jit.cubin.data(), nullptr, nullptr, 0,
+                                 nullptr, nullptr, 0));
+    if (cudaLibraryGetKernel(&ex->initECS, ex->lib, "mb2_entry_init_ecs") != cudaSuccess ||
+        cudaLibraryGetKernel(&ex->initWorlds, ex->lib, "mb2_entry_init_worlds") != cudaSuccess ||
+        cudaLibraryGetKernel(&ex->initTasks, ex->lib, "mb2_entry_init_tasks") != cudaSuccess) {
+        cudaGetLastError();
+        setError("simulator module lacks MADRONA_BUILD_MWGPU_ENTRY(...) entry points");
+        return false;
+    }
+    for (size_t i = 0; i < ex->jit.nodeKernels.size(); i++) {
+        cudaKernel_t k;
+        MB2_CUDA(cudaLibraryGetKernel(&k, ex->lib, ex->jit.nodeKernels[i].c_str()));
+        void *meta = nullptr;
+        size_t meta_bytes = 0;
+        MB2_CUDA(cudaLibraryGetGlobal(&meta, &meta_bytes, ex->lib, ex->jit.nodeMetas[i].c_str()));
+        ex->nodeKernels.push_back(k);
+        ex->nodeMetaAddrs.push_back((uint64_t)(uintptr_t)meta);
+    }
+
+    // ---- engine state block
+    ex->hState = (EngineState *)calloc(1, sizeof(EngineState));
+    MB2_CUDA(cudaMalloc((void **)&ex->dState, sizeof(EngineState)));
+    ex->allocations.push_back(ex->dState);
+    MB2_CUDA(cudaMemset(ex->dState, 0, sizeof(EngineState)));
+    MB2_CUDA(cudaMallocHost((void **)&ex->hStatus, 64));
+    memset(ex->hStatus, 0, 64);
+
+    EngineState &S = *ex->hState;
+    S.numWorlds = sc->num_worlds;
+    S.numTaskGraphs = sc->num_taskgraphs;
+    S.numExported = sc->num_exported_buffers;
+    if (!devAlloc(ex, &S.userConfig, std::max(sc->num_user_config_bytes, 16u))) return false;
+    if (sc->num_user_config_bytes)
+        MB2_CUDA(cudaMemcpy(S.userConfig, sc->user_config_ptr, sc->num_user_config_bytes,
+                            cudaMemcpyHostToDevice));
+    S.worldInitBytes = sc->num_world_init_bytes;
+    size_t init_bytes = (size_t)sc->num_world_init_bytes * sc->num_worlds;
+    if (!devAlloc(ex, &S.worldInits, std::max(init_bytes, (size_t)16))) return false;
+    if (init_bytes)
+        MB2_CUDA(cudaMemcpy(S.worldInits, sc->world_init_ptr, init_bytes, cudaMemcpyHostToDevice));
+
+    // engine-owned systems get their device blocks before registerTypes so the
+    // simulator's calls into PhysicsSystem / RenderingSystem can record into them
+    if (!physicsHostCreate(ex, &err)) {
+        setError(err);
+        return false;
+    }
+    if (!pushState(ex)) return false;
+
+    void *state_sym = nullptr;
+    size_t state_sym_bytes = 0;
+    MB2_CUDA(cudaLibraryGetGlobal(&state_sym, &state_sym_bytes, ex->lib, "mb2_engine_state"));
+    MB2_CUDA(cudaMemcpy(state_sym, &ex->dState, sizeof(void *), cudaMemcpyHostToDevice));
+
+    // ---- phase 1: registerTypes on the device (1 thread)
+    if (!launch1(ex, ex->initECS, 1, 1)) return false;
+    if (!pullState(ex)) return false;
+    if (!checkDeviceErrors(ex, "registerTypes")) return false;
+
+    // ---- phase 2: storage.  numWorldDataBytes == 0 means "use sizeof(WorldT) as
+    // the device compiler sees it" (the only size that matters here).
+    {
+        uint32_t bytes = sc->num_world_data_bytes ? sc->num_world_data_bytes : S.worldDataNeeded;
+        if (bytes < S.worldDataNeeded) {
+            setError("StateConfig::numWorldDataBytes (" + std::to_string(bytes) +
+                     ") is smaller than the simulator's per-world data type (" +
+                     std::to_string(S.worldDataNeeded) + ")");
+            return false;
+        }
+        uint32_t align = std::max({ sc->world_data_alignment, S.worldDataAlignNeeded, 16u });
+        S.worldDataStride = (bytes + align - 1) / align * align;
+        if (!devAlloc(ex, (void **)&S.worldData, (size_t)S.worldDataStride * S.numWorlds)) return false;
+    }
+    if (!allocateTables(ex)) return false;
+    if (!sortScratchCreate(ex, &err)) {
+        setError(err);
+        return false;
+    }
+    if (!physicsHostAfterRegistry(ex, rc, &err)) {
+        setError(err);
+        return false;
+    }
+    const uint64_t persist_mark = ex->hState->persistOffset;
+
+    // ---- phase 3: world constructors, two passes (see mb2_state.h IDCache)
+    const unsigned wblocks = (S.numWorlds + 127) / 128;
+    if (!resetForInitPass(ex, 0, {}, persist_mark)) return false;
+    if (!launch1(ex, ex->initWorlds, wblocks, 128)) return false;
+    if (!checkDeviceErrors(ex, "world construction (dry run)")) return false;
+
+    std::vector<IDCache> caches(S.numWorlds);
+    MB2_CUDA(cudaMemcpy(caches.data(), S.idCaches, sizeof(IDCache) * S.numWorlds,
+                        cudaMemcpyDeviceToHost));
+    std::vector<int32_t> expand_base(S.numWorlds);
+    int64_t next_block = S.initExpandBlocks;
+    for (uint32_t w = 0; w < S.numWorlds; w++) {
+        expand_base[w] = (int32_t)next_block;
+        next_block += caches[w].numExpands;
+    }
+    if (next_block * kIDsPerCache > S.entityCapacity) {
+        setError("entity store too small for world construction");
+        return false;
+    }
+    if (!resetForInitPass(ex, 1, expand_base, persist_mark)) return false;
+    if (!launch1(ex, ex->initWorlds, wblocks, 128)) return false;
+    if (!checkDeviceErrors(ex, "world construction")) return false;
+    if (!pullState(ex)) return false;
+    S.numEntitySlots = (int32_t)(next_block * kIDsPerCache);
+    S.initPass = 2;
+    if (!pushState(ex)) return false;
+
+    // ---- phase 4: setupTasks on the device (1 thread)
+    if (!launch1(ex, ex->initTasks, 1, 1)) return false;
+    if (!pullState(ex)) return false;
+    if (!checkDeviceErrors(ex, "setupTasks")) return false;
+
+    // resolve ParallelFor records to kernels
+    for (uint32_t n = 0; n < S.numNodes; n++) {
+        NodeRecord &r = S.nodes[n];
+        if (r.kind != NodeUserParallelFor) continue;
+        uint64_t addr = ((uint64_t)r.component << 32) | r.kernelID;
+        size_t k = 0;
+        for (; k < ex->nodeMetaAddrs.size(); k++) {
+            if (ex->nodeMetaAddrs[k] == addr) break;
+        }
+        if (k == ex->nodeMetaAddrs.size()) {
+            setError("taskgraph node " + std::to_string(n) + " has no kernel in the module");
+            return false;
+        }
+        r.kernelID = (uint32_t)k;
+    }
+    MB2_CUDA(cudaMemcpy(ex->dState->nodes, S.nodes, sizeof(NodeRecord) * S.numNodes,
+                        cudaMemcpyHostToDevice));
+
+    // ---- phase 5: bring every table into world order so exported columns are
+    // world-major from step 0 (the CPU backend's layout, src/core/state.cpp:576-619)
+    for (uint32_t a = 0; a < S.numArchetypes; a++) {
+        if (!S.archetypes[a].registered || S.tables[a].isSingleton) continue;
+        launchSortArchetype(ex, a, 1, ex->stream);
+    }
+    MB2_CUDA(cudaStreamSynchronize(ex->stream));
+    MB2_CUDA(cudaGetLastError());
+    if (!checkDeviceErrors(ex, "initial sort")) return false;
+    return true;
+}
+
+static void destroyExecutor(Executor *ex)
+{
+    if (!ex) return;
+    cudaSetDevice(ex->gpu);
+    if (ex->stream) cudaStreamSynchronize(ex->stream);
+    physicsHostDestroy(ex);
+    sortScratchDestroy(ex);
+    for (void *p : ex->allocations) cudaFree(p);
+    if (ex->hStatus) cudaFreeHost(ex->hStatus);
+    if (ex->lib) cudaLibraryUnload(ex->lib);
+    if (ex->stream) cudaStreamDestroy(ex->stream);
+    free(ex->hState);
+    delete ex;
+}
+
+// ---- launch graphs -----------------------------------------------------------
+
+static bool enqueueNode(Executor *ex, uint32_t node_idx, cudaStream_t s)
+{
+    EngineState &S = *ex->hState;
+    const NodeRecord &r = S.nodes[node_idx];
+    switch (r.kind) {
+    case NodeUserParallelFor: {
+        const TableDesc &t = S.tables[r.archetype];
+        uint64_t threads = (uint64_t)t.capacity * std::max(r.userTag, 1u);
+        uint64_t blocks = (threads + 255) / 256;
+        uint64_t max_blocks = (uint64_t)ex->numSMs * 8;
+        unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(blocks, max_blocks));
+        const NodeRecord *drec = &ex->dState->nodes[node_idx];
+        void *args[1] = { (void *)&drec };
+        MB2_CUDA(cudaLaunchKernel((const void *)ex->nodeKernels[r.kernelID], dim3(grid),
+                                  dim3(256), args, 0, s));
+        return true;
+    }
+    case NodeSortArchetype:
+    case NodeCompactArchetype: {
+        int32_t col = 1;
+        if (r.kind == NodeSortArchetype) {
+            if (r.component >= S.numComponents || S.columnLookup[r.archetype][r.component] < 0) {
+                setError("SortArchetypeNode: archetype lacks the sort component");
+                return false;
+            }
+            col = S.columnLookup[r.archetype][r.component];
+        }
+        launchSortArchetype(ex, r.archetype, col, s);
+        return true;
+    }
+    case NodeClearTmp:
+        launchClearTmp(ex, r.archetype, s);
+        return true;
+    case NodeResetTmpAlloc:
+        if (r.userTag == 0xFFFFFFFFu) return true;   // placeholder for an empty query
+        launchResetTmpAlloc(ex, s);
+        return true;
+    case NodeRecycleEntities:
+        // IDs are recycled at destroy time through the per-world caches
+        // (state.hpp releaseEntityLocked); nothing left to do here.
+        return true;
+    default:
+        if (r.kind >= NodePhysBroadphaseUpdate) {
+            std::string err;
+            if (!physicsEnqueueNode(ex, r, s, &err)) {
+                setError(err);
+                return false;
+            }
+            return true;
+        }
+        setError("unknown taskgraph node kind " + std::to_string(r.kind));
+        return false;
+    }
+}
+
+static LaunchGraph *buildGraph(Executor *ex, const uint32_t *ids, uint32_t n, const char *name)
+{
+    EngineState &S = *ex->hState;
+    cudaSetDevice(ex->gpu);
+    LaunchGraph *g = new LaunchGraph();
+    g->owner = ex;
+    g->name = name ? name : "";
+
+    cudaError_t e = cudaStreamBeginCapture(ex->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        setError(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+        delete g;
+        return nullptr;
+    }
+    bool ok = true;
+    for (uint32_t i = 0; i < n && ok; i++) {
+        if (ids[i] >= S.numTaskGraphs) {
+            setError("taskgraph id out of range");
+            ok = false;
+            break;
+        }
+        for (uint32_t node = 0; node < S.numNodes && ok; node++) {
+            if (S.nodes[node].taskgraph != ids[i]) continue;
+            ok = enqueueNode(ex, node, ex->stream);
+        }
+    }
+    if (ok) launchStatusCopy(ex, ex->stream);
+    e = cudaStreamEndCapture(ex->stream, &g->graph);
+    if (!ok || e != cudaSuccess) {
+        if (ok) setError(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        if (g->graph) cudaGraphDestroy(g->graph);
+        delete g;
+        return nullptr;
+    }
+    size_t num_nodes = 0;
+    cudaGraphGetNodes(g->graph, nullptr, &num_nodes);
+    std::vector<cudaGraphNode_t> nodes(num_nodes);
+    if (num_nodes) cudaGraphGetNodes(g->graph, nodes.data(), &num_nodes);
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel)
+            g->numKernels++;
+    }
+    e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) {
+        setError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        cudaGraphDestroy(g->graph);
+        delete g;
+        return nullptr;
+    }
+    return g;
+}
+
+}
+
+using namespace mb2;
+
+extern "C" {
+
+const char *mb2_last_error(void) { return g_last_error.c_str(); }
+
+const char *mb2_version(void) { return "madrona_b200 0.1 (sm_100a)"; }
+
+int mb2_init_cuda(int gpu_id)
+{
+    cudaError_t e = cudaSetDevice(gpu_id);
+    if (e != cudaSuccess) {
+        setError(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    cudaFree(nullptr);
+    return 0;
+}
+
+mb2_executor *mb2_executor_create(const mb2_state_config *state_cfg,
+                                  const mb2_compile_config *compile_cfg,
+                                  int gpu_id, const mb2_render_config *render_cfg)
+{
+    g_last_error.clear();
+    if (!state_cfg || !compile_cfg) {
+        setError("null config");
+        return nullptr;
+    }
+    Executor *ex = new Executor();
+    ex->gpu = gpu_id;
+    if (!createExecutor(ex, state_cfg, compile_cfg, render_cfg)) {
+        std::string keep = g_last_error;
+        destroyExecutor(ex);
+        g_last_error = keep;
+        return nullptr;
+    }
+    return (mb2_executor *)ex;
+}
+
+void mb2_executor_destroy(mb2_executor *exec) { destroyExecutor((Executor *)exec); }
+
+mb2_launch_graph *mb2_build_launch_graph(mb2_executor *exec, const uint32_t *taskgraph_ids,
+                                         uint32_t num_taskgraphs, const char *stat_name)
+{
+    g_last_error.clear();
+    return (mb2_launch_graph *)buildGraph((Executor *)exec, taskgraph_ids, num_taskgraphs, stat_name);
+}
+
+mb2_launch_graph *mb2_build_launch_graph_all(mb2_executor *exec)
+{
+    Executor *ex = (Executor *)exec;
+    std::vector<uint32_t> ids(ex->hState->numTaskGraphs);
+    for (uint32_t i = 0; i < ids.size(); i++) ids[i] = i;
+    return mb2_build_launch_graph(exec, ids.data(), (uint32_t)ids.size(), "all");
+}
+
+mb2_launch_graph *mb2_build_render_graph(mb2_executor *exec)
+{
+    g_last_error.clear();
+    Executor *ex = (Executor *)exec;
+    std::string err;
+    LaunchGraph *g = physicsBuildRenderGraph(ex, &err);
+    if (!g) setError(err);
+    return (mb2_launch_graph *)g;
+}
+
+void mb2_launch_graph_destroy(mb2_launch_graph *graph)
+{
+    LaunchGraph *g = (LaunchGraph *)graph;
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+
+int mb2_run_async(mb2_executor *exec, mb2_launch_graph *graph, void *cuda_stream)
+{
+    Executor *ex = (Executor *)exec;
+    LaunchGraph *g = (LaunchGraph *)graph;
+    if (!ex || !g) {
+        setError("null executor or launch graph");
+        return 1;
+    }
+    cudaError_t e = cudaGraphLaunch(g->exec, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) {
+        setError(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+int mb2_run(mb2_executor *exec, mb2_launch_graph *graph)
+{
+    Executor *ex = (Executor *)exec;
+    if (mb2_run_async(exec, graph, ex ? ex->stream : nullptr) != 0) return 1;
+    cudaError_t e = cudaStreamSynchronize(ex->stream);
+    if (e != cudaSuccess) {
+        setError(std::string("step failed: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    if (ex->hStatus[0] != 0) {
+        setError("step failed: " + describeErrors(ex->hStatus[0], ex->hStatus[1]));
+        return 2;
+    }
+    return 0;
+}
+
+void *mb2_get_exported(const mb2_executor *exec, int64_t slot)
+{
+    const Executor *ex = (const Executor *)exec;
+    if (!ex || slot < 0 || slot >= kMaxExports) return nullptr;
+    return ex->exported[slot];
+}
+
+int64_t mb2_get_exported_num_rows(mb2_executor *exec, int64_t slot)
+{
+    Executor *ex = (Executor *)exec;
+    if (!ex || slot < 0 || slot >= kMaxExports || !ex->exported[slot]) return -1;
+    int32_t n = 0;
+    cudaStreamSynchronize(ex->stream);
+    cudaMemcpy(&n, &ex->dState->tables[ex->exportArchetype[slot]].numRows, sizeof(n),
+               cudaMemcpyDeviceToHost);
+    return n;
+}
+
+int64_t mb2_get_exported_row_bytes(const mb2_executor *exec, int64_t slot)
+{
+    const Executor *ex = (const Executor *)exec;
+    if (!ex || slot < 0 || slot >= kMaxExports || !ex->exported[slot]) return -1;
+    return ex->exportRowBytes[slot];
+}
+
+int64_t mb2_launch_graph_num_kernels(const mb2_launch_graph *graph)
+{
+    return graph ? ((const LaunchGraph *)graph)->numKernels : -1;
+}
+
+void *mb2_executor_stream(mb2_executor *exec)
+{
+    return exec ? (void *)((Executor *)exec)->stream : nullptr;
+}
+
+int mb2_jit_precompile(const mb2_compile_config *cc)
+{
+    g_last_error.clear();
+    std::vector<std::string> sources, flags;
+    for (uint32_t i = 0; i < cc->num_user_sources; i++) sources.push_back(cc->user_sources[i]);
+    for (uint32_t i = 0; i < cc->num_user_compile_flags; i++) flags.push_back(cc->user_compile_flags[i]);
+    JitModule m;
+    std::string err;
+    if (!jitCompile(sources, flags, (int)cc->opt_mode, &m, &err)) {
+        setError(err);
+        return 1;
+    }
+    return 0;
+}
+
+}

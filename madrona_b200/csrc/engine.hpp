@@ -1,0 +1,67 @@
+// engine.hpp -- host-side executor state behind the C ABI (include/madrona_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "mb2_state.h"
+#include "jit.hpp"
+
+namespace mb2 {
+
+struct SortScratch;   // kernels_sort.cu
+struct PhysicsHost;   // kernels_physics.cu
+struct RenderHost;    // kernels_render.cu
+
+struct Executor {
+    int gpu = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+
+    JitModule jit;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t initECS = nullptr, initWorlds = nullptr, initTasks = nullptr;
+    std::vector<cudaKernel_t> nodeKernels;
+    std::vector<uint64_t> nodeMetaAddrs;
+
+    EngineState *dState = nullptr;     // device
+    EngineState *hState = nullptr;     // host mirror (registry, nodes, table descs)
+    uint32_t *hStatus = nullptr;       // pinned: [0] errorFlags, [1] errorArchetype
+
+    std::vector<void *> allocations;   // cudaMalloc'd blocks owned by the executor
+    void *exported[kMaxExports] = {};
+    uint32_t exportArchetype[kMaxExports] = {};
+    uint32_t exportRowBytes[kMaxExports] = {};
+
+    SortScratch *sortScratch = nullptr;
+    PhysicsHost *physics = nullptr;
+    RenderHost *render = nullptr;
+
+    uint64_t rowsPerWorldHint = 64;
+};
+
+struct LaunchGraph {
+    Executor *owner = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int64_t numKernels = 0;
+    std::string name;
+};
+
+void setError(const std::string &msg);
+
+// ---- ahead-of-time engine kernels (kernels_core.cu / kernels_sort.cu) -----
+void launchClearTmp(Executor *ex, uint32_t archetype, cudaStream_t s);
+void launchResetTmpAlloc(Executor *ex, cudaStream_t s);
+void launchStatusCopy(Executor *ex, cudaStream_t s);
+void launchFillSingletons(Executor *ex, cudaStream_t s);
+
+bool sortScratchCreate(Executor *ex, std::string *err);
+void sortScratchDestroy(Executor *ex);
+// Stable sort of `archetype` by the low bits of column `col`; col==1 (WorldID)
+// additionally drops rows with key -1 and rebuilds worldOffsets/worldCounts.
+void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStream_t s);
+
+}

@@ -1,0 +1,543 @@
+// kernels_sort.cu -- hot system 1: stable radix sort / compaction of an
+// archetype table (all worlds' rows) + fused multi-column permutation.
+//
+// Semantics follow the reference GPU sort (src/mw/device/sort_archetype.cpp
+// :977-1551): key = first 4 bytes of the sort column compared on
+// the low 8*P bits, stable LSD; for WorldID sorts rows with key -1 (destroyed)
+// sort last and are truncated, worldOffsets/worldCounts are rebuilt (empty
+// worlds: offset = numRows, count = 0), entity slots are re-pointed, and the
+// whole thing is skipped when !needsSort.
+//
+// Mechanism is new (the reference expands one sort into ~40 megakernel nodes
+// with a device-wide barrier between each and moves every column twice with
+// per-element memcpy):
+//   1 histogram kernel  (all passes' digit histograms in one read of the keys)
+//   P onesweep kernels  (decoupled look-back, ticketed persistent tiles,
+//                        warp match-any ranking -> stable)
+//   1 rearrange kernel  (ALL columns in one launch, each column read once and
+//                        written once into its twin buffer; the table's column
+//                        pointers are flipped on the device, so no copy-back;
+//                        also entity remap + offsets/counts + scratch reset)
+// => P+2 launches per sort.  Exported columns must keep their address, so
+// they (only) get one extra copy-back launch.
+#include "engine.hpp"
+#include <cstdio>
+
+namespace mb2 {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kItemsPerThread = 8;
+constexpr int kTileItems = kSortThreads * kItemsPerThread;   // 2048
+constexpr int kMaxPasses = 4;
+
+struct SortCtrl {
+    int32_t tickets[kMaxPasses];
+    int32_t numDeleted;
+    int32_t blocksDone;
+    int32_t didSort;
+    int32_t copyBlocksDone;
+};
+
+struct SortScratch {
+    uint32_t *keys[2] = {};
+    int32_t *idx[2] = {};
+    int32_t *bins = nullptr;        // [kMaxPasses][256]
+    uint32_t *lookback = nullptr;   // [kMaxPasses][maxTiles][256]
+    SortCtrl *ctrl = nullptr;
+    void **altColumns = nullptr;    // device [kMaxArchetypes][kMaxColumns]
+    uint8_t exportedMask[kMaxArchetypes][kMaxColumns] = {};
+    bool hasExported[kMaxArchetypes] = {};
+    int32_t maxTiles = 0;
+    int32_t maxCapacity = 0;
+};
+
+struct SortParams {
+    EngineState *state;
+    uint32_t archetype;
+    int32_t keyCol;
+    int32_t numPasses;
+    int32_t worldSort;
+    uint32_t *keys[2];
+    int32_t *idx[2];
+    int32_t *bins;
+    uint32_t *lookback;
+    SortCtrl *ctrl;
+    void **alt;       // this archetype's row of altColumns
+    int32_t maxTiles;
+    int32_t hasExported;
+};
+
+__device__ __forceinline__ bool sortActive(const SortParams &p, const TableDesc &t)
+{
+    // WorldID sorts are skipped for clean tables (sort_archetype.cpp:988-997);
+    // custom-key sorts always run.
+    return !p.worldSort || t.needsSort != 0;
+}
+
+__device__ __forceinline__ uint32_t loadKey(const TableDesc &t, int32_t col, int32_t row)
+{
+    const char *base = (const char *)t.columns[col];
+    return *(const uint32_t *)(base + (size_t)row * t.columnBytes[col]);
+}
+
+// ---- kernel 1: digit histograms for every pass + deleted-row count -----------
+__global__ void __launch_bounds__(kSortThreads)
+sortHistogramKernel(SortParams p)
+{
+    const TableDesc &t = p.state->tables[p.archetype];
+    if (!sortActive(p, t)) return;
+    const int32_t n = t.numRows;
+
+    __shared__ uint32_t hist[kMaxPasses][256];
+    __shared__ uint32_t deleted;
+    for (int i = threadIdx.x; i < kMaxPasses * 256; i += blockDim.x) (&hist[0][0])[i] = 0;
+    if (threadIdx.x == 0) deleted = 0;
+    __syncthreads();
+
+    uint32_t my_deleted = 0;
+    for (int32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n;
+         row += gridDim.x * blockDim.x) {
+        uint32_t key = loadKey(t, p.keyCol, row);
+        if (key == 0xFFFFFFFFu) my_deleted++;
+        for (int pass = 0; pass < p.numPasses; pass++) {
+            atomicAdd(&hist[pass][(key >> (8 * pass)) & 0xffu], 1u);
+        }
+    }
+    if (my_deleted) atomicAdd(&deleted, my_deleted);
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < p.numPasses * 256; i += blockDim.x) {
+        uint32_t v = (&hist[0][0])[i];
+        if (v) atomicAdd(&p.bins[i], (int32_t)v);
+    }
+    if (threadIdx.x == 0 && deleted && p.worldSort) atomicAdd(&p.ctrl->numDeleted, (int32_t)deleted);
+}
+
+// ---- kernels 2..P+1: one onesweep pass -------------------------------------------
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagInclusive = 2u << 30;
+constexpr uint32_t kValueMask = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(kSortThreads)
+sortOnesweepKernel(SortParams p, int pass)
+{
+    const TableDesc &t = p.state->tables[p.archetype];
+    if (!sortActive(p, t)) return;
+    const int32_t n = t.numRows;
+    const int32_t num_tiles = (n + kTileItems - 1) / kTileItems;
+    const bool last_pass = pass == p.numPasses - 1;
+
+    // Side job of the last pass of a world sort: defaults for empty worlds
+    // (offset = new numRows, count = 0; sort_archetype.cpp:1269-1337).
+    if (last_pass && p.worldSort) {
+        const int32_t new_n = n - p.ctrl->numDeleted;
+        const int32_t W = (int32_t)p.state->numWorlds;
+        for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < W;
+             w += gridDim.x * blockDim.x) {
+            t.worldOffsets[w] = new_n;
+            t.worldCounts[w] = 0;
+        }
+    }
+
+    const uint32_t *keys_in = p.keys[(pass + 1) & 1];
+    const int32_t *idx_in = p.idx[(pass + 1) & 1];
+    uint32_t *keys_out = p.keys[pass & 1];
+    int32_t *idx_out = p.idx[pass & 1];
+    uint32_t *lookback = p.lookback + (size_t)pass * p.maxTiles * 256;
+    const int shift = 8 * pass;
+
+    __shared__ uint32_t warp_hist[kSortWarps][256];
+    __shared__ uint32_t digit_base[256];
+    __shared__ uint32_t scan_tmp[kSortWarps];
+    __shared__ int32_t tile_s;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    // exclusive scan of this pass's global digit histogram (256 bins)
+    uint32_t bin_excl;
+    {
+        uint32_t v = (uint32_t)p.bins[pass * 256 + threadIdx.x];
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) scan_tmp[warp] = incl;
+        __syncthreads();
+        uint32_t warp_off = 0;
+        for (int w = 0; w < warp; w++) warp_off += scan_tmp[w];
+        bin_excl = warp_off + incl - v;
+        __syncthreads();
+    }
+
+    while (true) {
+        if (threadIdx.x == 0) tile_s = atomicAdd(&p.ctrl->tickets[pass], 1);
+        for (int i = threadIdx.x; i < kSortWarps * 256; i += blockDim.x) (&warp_hist[0][0])[i] = 0;
+        __syncthreads();
+        const int32_t tile = tile_s;
+        if (tile >= num_tiles) break;
+
+        // -- load + stable rank inside the warp's 256-item strip
+        uint32_t key[kItemsPerThread];
+        int32_t idx[kItemsPerThread];
+        uint32_t rank[kItemsPerThread];
+        const int32_t strip = tile * kTileItems + warp * (32 * kItemsPerThread);
+#pragma unroll
+        for (int r = 0; r < kItemsPerThread; r++) {
+            const int32_t i = strip + r * 32 + lane;
+            const bool valid = i < n;
+            uint32_t k = 0;
+            int32_t src = i;
+            if (valid) {
+                if (pass == 0) {
+                    k = loadKey(t, p.keyCol, i);
+                } else {
+                    k = keys_in[i];
+                    src = idx_in[i];
+                }
+            }
+            key[r] = k;
+            idx[r] = src;
+            const uint32_t digit = (k >> shift) & 0xffu;
+            const uint32_t match_val = valid ? digit : (0x100u + (uint32_t)lane);
+            const uint32_t peers = __match_any_sync(0xffffffffu, match_val);
+            const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+            uint32_t base = 0;
+            if (valid) base = warp_hist[warp][digit];
+            __syncwarp();
+            if (valid && before == 0) warp_hist[warp][digit] = base + __popc(peers);
+            __syncwarp();
+            rank[r] = valid ? base + before : 0xFFFFFFFFu;
+        }
+        __syncthreads();
+
+        // -- per digit (thread d): offsets of each warp inside the tile, tile total
+        const int d = threadIdx.x;
+        uint32_t tile_count = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) {
+            uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = tile_count;
+            tile_count += c;
+        }
+
+        // -- decoupled look-back across tiles for digit d
+        volatile uint32_t *lb = lookback;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            lb[d] = kFlagInclusive | tile_count;
+        } else {
+            lb[(size_t)tile * 256 + d] = kFlagAggregate | tile_count;
+            __threadfence();
+            int32_t look = tile - 1;
+            while (true) {
+                uint32_t v = lb[(size_t)look * 256 + d];
+                if ((v >> 30) == 0) continue;     // predecessor not published yet
+                excl += v & kValueMask;
+                if ((v >> 30) == 2u) break;
+                look--;
+            }
+            lb[(size_t)tile * 256 + d] = kFlagInclusive | (excl + tile_count);
+        }
+        digit_base[d] = bin_excl + excl;
+        __syncthreads();
+
+        // -- scatter
+#pragma unroll
+        for (int r = 0; r < kItemsPerThread; r++) {
+            if (rank[r] == 0xFFFFFFFFu) continue;
+            const uint32_t digit = (key[r] >> shift) & 0xffu;
+            const uint32_t pos = digit_base[digit] + warp_hist[warp][digit] + rank[r];
+            keys_out[pos] = key[r];
+            idx_out[pos] = idx[r];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- kernel P+2: fused multi-column permutation ------------------------------------
+template <typename UnitT>
+__device__ __forceinline__ void gatherUnits(const void *src_v, void *dst_v,
+                                            const int32_t *perm, int32_t new_n,
+                                            uint32_t units_per_row,
+                                            int64_t first, int64_t stride)
+{
+    const UnitT *src = (const UnitT *)src_v;
+    UnitT *dst = (UnitT *)dst_v;
+    const int64_t total = (int64_t)new_n * units_per_row;
+    if (units_per_row == 1) {
+        for (int64_t u = first; u < total; u += stride) dst[u] = src[perm[u]];
+    } else {
+        for (int64_t u = first; u < total; u += stride) {
+            const int32_t row = (int32_t)(u / units_per_row);
+            const uint32_t k = (uint32_t)(u - (int64_t)row * units_per_row);
+            dst[u] = src[(int64_t)perm[row] * units_per_row + k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sortRearrangeKernel(SortParams p)
+{
+    TableDesc &t = p.state->tables[p.archetype];
+    if (!sortActive(p, t)) return;
+    const int32_t n = t.numRows;
+    const int32_t new_n = p.worldSort ? n - p.ctrl->numDeleted : n;
+    const int last = (p.numPasses - 1) & 1;
+    const int32_t *perm = p.idx[last];
+    const uint32_t *sorted_keys = p.keys[last];
+    const int32_t col = blockIdx.y;
+
+    if (col < t.numColumns) {
+        const void *src = t.columns[col];
+        void *dst = p.alt[col];
+        const uint32_t bytes = t.columnBytes[col];
+        const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+
+        if (col == 0) {
+            // Entity column: move + re-point the entity slot at the new row
+            // (sort_archetype.cpp:1357-1379)
+            const unsigned long long *s = (const unsigned long long *)src;
+            unsigned long long *d = (unsigned long long *)dst;
+            EntitySlot *slots = p.state->entitySlots;
+            for (int64_t r = first; r < new_n; r += stride) {
+                unsigned long long e = s[perm[r]];
+                d[r] = e;
+                const uint32_t gen = (uint32_t)(e & 0xFFFFFFFFull);
+                const int32_t id = (int32_t)(uint32_t)(e >> 32);
+                if (id >= 0 && gen != 0xFFFFFFFFu && id < p.state->entityCapacity &&
+                        slots[id].gen == gen && slots[id].a == (int32_t)p.archetype) {
+                    slots[id].b = (int32_t)r;
+                }
+            }
+        } else if ((bytes & 15u) == 0) {
+            gatherUnits<uint4>(src, dst, perm, new_n, bytes >> 4, first, stride);
+        } else if ((bytes & 7u) == 0) {
+            gatherUnits<uint2>(src, dst, perm, new_n, bytes >> 3, first, stride);
+        } else if ((bytes & 3u) == 0) {
+            gatherUnits<uint32_t>(src, dst, perm, new_n, bytes >> 2, first, stride);
+        } else {
+            gatherUnits<unsigned char>(src, dst, perm, new_n, bytes, first, stride);
+        }
+
+        // world boundaries from the sorted keys (done by the WorldID column's blocks)
+        if (col == 1 && p.worldSort) {
+            for (int64_t r = first; r < new_n; r += stride) {
+                const uint32_t k = sorted_keys[r];
+                if (r == 0 || sorted_keys[r - 1] != k) {
+                    int32_t end = (int32_t)r + 1;
+                    while (end < new_n && sorted_keys[end] == k) end++;
+                    t.worldOffsets[k] = (int32_t)r;
+                    t.worldCounts[k] = end - (int32_t)r;
+                }
+            }
+        }
+    }
+
+    // ---- last block out: flip column buffers, publish the new row count,
+    // reset the scratch for the next sort.
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t done = atomicAdd(&p.ctrl->blocksDone, 1);
+        is_last = done == (int32_t)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    for (int c = threadIdx.x; c < t.numColumns; c += blockDim.x) {
+        void *old_main = t.columns[c];
+        t.columns[c] = p.alt[c];
+        p.alt[c] = old_main;
+    }
+    for (int i = threadIdx.x; i < p.numPasses * 256; i += blockDim.x) p.bins[i] = 0;
+    const int32_t tiles = (n + kTileItems - 1) / kTileItems;
+    for (int pass = 0; pass < p.numPasses; pass++) {
+        uint32_t *lb = p.lookback + (size_t)pass * p.maxTiles * 256;
+        for (int64_t i = threadIdx.x; i < (int64_t)tiles * 256; i += blockDim.x) lb[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        t.numRows = new_n;
+        if ((uint32_t)n > t.highWater) t.highWater = (uint32_t)n;
+        // a custom-key sort leaves the table out of world order
+        // (sort_archetype.cpp:1003-1007)
+        t.needsSort = p.worldSort ? 0u : 1u;
+        for (int i = 0; i < kMaxPasses; i++) p.ctrl->tickets[i] = 0;
+        p.ctrl->numDeleted = 0;
+        p.ctrl->blocksDone = 0;
+        p.ctrl->didSort = p.hasExported;
+    }
+}
+
+// Exported columns must keep their address: after the flip their data sits in
+// the twin buffer, so copy it back and flip those pointers again.
+__global__ void __launch_bounds__(256)
+sortCopyBackKernel(SortParams p, unsigned long long exported_mask)
+{
+    TableDesc &t = p.state->tables[p.archetype];
+    if (!p.ctrl->didSort) return;
+    const int32_t n = t.numRows;
+    const int32_t col = blockIdx.y;
+    if (col < t.numColumns && ((exported_mask >> col) & 1ull)) {
+        // after the flip: t.columns[col] = twin (holds data), p.alt[col] = exported address
+        const uint32_t *src = (const uint32_t *)t.columns[col];
+        uint32_t *dst = (uint32_t *)p.alt[col];
+        const int64_t words = ((int64_t)n * t.columnBytes[col] + 3) / 4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            dst[i] = src[i];
+        }
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t done = atomicAdd(&p.ctrl->copyBlocksDone, 1);
+        is_last = done == (int32_t)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < t.numColumns; c += blockDim.x) {
+        if ((exported_mask >> c) & 1ull) {
+            void *twin = t.columns[c];
+            t.columns[c] = p.alt[c];
+            p.alt[c] = twin;
+        }
+    }
+    if (threadIdx.x == 0) {
+        p.ctrl->copyBlocksDone = 0;
+        p.ctrl->didSort = 0;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------
+
+bool sortScratchCreate(Executor *ex, std::string *err)
+{
+    EngineState &S = *ex->hState;
+    SortScratch *sc = new SortScratch();
+    ex->sortScratch = sc;
+
+    int32_t max_cap = 256;
+    for (uint32_t a = 0; a < S.numArchetypes; a++) {
+        if (S.archetypes[a].registered && !S.tables[a].isSingleton)
+            max_cap = std::max(max_cap, S.tables[a].capacity);
+    }
+    sc->maxCapacity = max_cap;
+    sc->maxTiles = (max_cap + kTileItems - 1) / kTileItems + 1;
+
+    auto alloc = [&](void **p, size_t bytes) {
+        if (cudaMalloc(p, bytes) != cudaSuccess) return false;
+        ex->allocations.push_back(*p);
+        cudaMemsetAsync(*p, 0, bytes, ex->stream);
+        return true;
+    };
+    bool ok = true;
+    for (int i = 0; i < 2; i++) {
+        ok = ok && alloc((void **)&sc->keys[i], sizeof(uint32_t) * (size_t)max_cap);
+        ok = ok && alloc((void **)&sc->idx[i], sizeof(int32_t) * (size_t)max_cap);
+    }
+    ok = ok && alloc((void **)&sc->bins, sizeof(int32_t) * kMaxPasses * 256);
+    ok = ok && alloc((void **)&sc->lookback, sizeof(uint32_t) * (size_t)kMaxPasses * sc->maxTiles * 256);
+    ok = ok && alloc((void **)&sc->ctrl, sizeof(SortCtrl));
+    ok = ok && alloc((void **)&sc->altColumns, sizeof(void *) * kMaxArchetypes * kMaxColumns);
+    if (!ok) {
+        *err = "sort scratch allocation failed";
+        return false;
+    }
+
+    for (uint32_t s = 0; s < S.numExported && s < (uint32_t)kMaxExports; s++) {
+        const ExportInfo &e = S.exports[s];
+        if (!e.used) continue;
+        int col = S.columnLookup[e.archetype][e.component];
+        sc->exportedMask[e.archetype][col] = 1;
+        sc->hasExported[e.archetype] = true;
+    }
+
+    // twin buffer for every column of every sortable table
+    std::vector<void *> alts((size_t)kMaxArchetypes * kMaxColumns, nullptr);
+    for (uint32_t a = 0; a < S.numArchetypes; a++) {
+        if (!S.archetypes[a].registered || S.tables[a].isSingleton) continue;
+        const TableDesc &t = S.tables[a];
+        for (int32_t c = 0; c < t.numColumns; c++) {
+            void *p = nullptr;
+            if (!alloc(&p, (size_t)t.columnBytes[c] * t.capacity + 256)) {
+                *err = "sort twin buffer allocation failed";
+                return false;
+            }
+            alts[(size_t)a * kMaxColumns + c] = p;
+        }
+    }
+    cudaMemcpyAsync(sc->altColumns, alts.data(), sizeof(void *) * alts.size(),
+                    cudaMemcpyHostToDevice, ex->stream);
+    cudaStreamSynchronize(ex->stream);
+    return true;
+}
+
+void sortScratchDestroy(Executor *ex)
+{
+    delete ex->sortScratch;
+    ex->sortScratch = nullptr;
+}
+
+static int worldSortPasses(uint32_t num_worlds)
+{
+    // every valid world ID must stay below the all-ones masked key of a
+    // destroyed row: W < 2^(8P)
+    int bits = 0;
+    while ((num_worlds >> bits) != 0) bits++;
+    int passes = (bits + 7) / 8;
+    return passes < 1 ? 1 : passes;
+}
+
+void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStream_t s)
+{
+    EngineState &S = *ex->hState;
+    SortScratch *sc = ex->sortScratch;
+    const TableDesc &t = S.tables[archetype];
+    if (t.isSingleton) return;
+
+    SortParams p;
+    p.state = ex->dState;
+    p.archetype = archetype;
+    p.keyCol = col;
+    p.worldSort = col == 1 ? 1 : 0;
+    p.numPasses = p.worldSort ? worldSortPasses(S.numWorlds) : 4;
+    p.keys[0] = sc->keys[0];
+    p.keys[1] = sc->keys[1];
+    p.idx[0] = sc->idx[0];
+    p.idx[1] = sc->idx[1];
+    p.bins = sc->bins;
+    p.lookback = sc->lookback;
+    p.ctrl = sc->ctrl;
+    p.alt = sc->altColumns + (size_t)archetype * kMaxColumns;
+    p.maxTiles = sc->maxTiles;
+
+    unsigned long long mask = 0;
+    for (int c = 0; c < t.numColumns; c++) {
+        if (sc->exportedMask[archetype][c]) mask |= 1ull << c;
+    }
+    p.hasExported = mask ? 1 : 0;
+
+    const int tiles = (t.capacity + kTileItems - 1) / kTileItems;
+    const int hist_grid = std::max(1, std::min(tiles, ex->numSMs * 4));
+    const int sweep_grid = std::max(1, std::min(tiles, ex->numSMs * 2));
+    sortHistogramKernel<<<hist_grid, kSortThreads, 0, s>>>(p);
+    for (int pass = 0; pass < p.numPasses; pass++) {
+        sortOnesweepKernel<<<sweep_grid, kSortThreads, 0, s>>>(p, pass);
+    }
+    const int row_blocks = std::max(1, std::min((t.capacity + 255) / 256, ex->numSMs * 2));
+    dim3 rgrid((unsigned)row_blocks, (unsigned)t.numColumns);
+    sortRearrangeKernel<<<rgrid, 256, 0, s>>>(p);
+
+    if (mask) sortCopyBackKernel<<<rgrid, 256, 0, s>>>(p, mask);
+}
+
+}

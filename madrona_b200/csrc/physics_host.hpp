@@ -1,0 +1,15 @@
+// Host hooks for the engine-owned systems (rigid-body physics, ray-cast
+// renderer): kernels_physics.cu / kernels_render.cu.
+#pragma once
+#include "engine.hpp"
+#include "../../include/madrona_b200.h"
+
+namespace mb2 {
+
+bool physicsHostCreate(Executor *ex, std::string *err);
+bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *rc, std::string *err);
+void physicsHostDestroy(Executor *ex);
+bool physicsEnqueueNode(Executor *ex, const NodeRecord &rec, cudaStream_t s, std::string *err);
+LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err);
+
+}

@@ -1,0 +1,323 @@
+"""ctypes binding of include/madrona_b200.h.
+
+Names and argument meaning follow the reference's host API
+(include/madrona/mw_gpu.hpp): StateConfig / CompileConfig fields are the same,
+MWCudaExecutor has buildLaunchGraph / buildLaunchGraphAllTaskGraphs / run /
+runAsync / getExported.  Errors that the reference turns into FATAL() (abort)
+are raised as MadronaB200Error here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+EXPORTED_SYMBOLS = [
+    "mb2_init_cuda",
+    "mb2_executor_create",
+    "mb2_executor_destroy",
+    "mb2_build_launch_graph",
+    "mb2_build_launch_graph_all",
+    "mb2_build_render_graph",
+    "mb2_launch_graph_destroy",
+    "mb2_run",
+    "mb2_run_async",
+    "mb2_get_exported",
+    "mb2_last_error",
+    "mb2_get_exported_num_rows",
+    "mb2_get_exported_row_bytes",
+    "mb2_launch_graph_num_kernels",
+    "mb2_executor_stream",
+    "mb2_jit_precompile",
+    "mb2_version",
+]
+
+
+class MadronaB200Error(RuntimeError):
+    pass
+
+
+class _StateConfigC(ctypes.Structure):
+    _fields_ = [
+        ("world_init_ptr", ctypes.c_void_p),
+        ("num_world_init_bytes", ctypes.c_uint32),
+        ("user_config_ptr", ctypes.c_void_p),
+        ("num_user_config_bytes", ctypes.c_uint32),
+        ("num_world_data_bytes", ctypes.c_uint32),
+        ("world_data_alignment", ctypes.c_uint32),
+        ("num_worlds", ctypes.c_uint32),
+        ("num_taskgraphs", ctypes.c_uint32),
+        ("num_exported_buffers", ctypes.c_uint32),
+    ]
+
+
+class _CompileConfigC(ctypes.Structure):
+    _fields_ = [
+        ("user_sources", ctypes.POINTER(ctypes.c_char_p)),
+        ("num_user_sources", ctypes.c_uint32),
+        ("user_compile_flags", ctypes.POINTER(ctypes.c_char_p)),
+        ("num_user_compile_flags", ctypes.c_uint32),
+        ("opt_mode", ctypes.c_uint32),
+    ]
+
+
+class _RenderConfigC(ctypes.Structure):
+    _fields_ = [
+        ("render_mode", ctypes.c_uint32),
+        ("render_resolution", ctypes.c_uint32),
+        ("near_plane", ctypes.c_float),
+        ("far_plane", ctypes.c_float),
+        ("mesh_bvhs", ctypes.c_void_p),
+        ("num_mesh_bvhs", ctypes.c_uint32),
+        ("vertices", ctypes.c_void_p),
+        ("num_vertices", ctypes.c_uint32),
+        ("indices", ctypes.c_void_p),
+        ("num_triangles", ctypes.c_uint32),
+    ]
+
+
+def library_path() -> str:
+    return os.path.join(_PKG_DIR, "libmadrona_b200.so")
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libmadrona_b200.so; fails loudly if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise MadronaB200Error(
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C madrona_b200`). There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    lib.mb2_init_cuda.argtypes = [ctypes.c_int]
+    lib.mb2_init_cuda.restype = ctypes.c_int
+    lib.mb2_executor_create.argtypes = [ctypes.POINTER(_StateConfigC),
+                                        ctypes.POINTER(_CompileConfigC),
+                                        ctypes.c_int, ctypes.POINTER(_RenderConfigC)]
+    lib.mb2_executor_create.restype = vp
+    lib.mb2_executor_destroy.argtypes = [vp]
+    lib.mb2_executor_destroy.restype = None
+    lib.mb2_build_launch_graph.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32),
+                                           ctypes.c_uint32, ctypes.c_char_p]
+    lib.mb2_build_launch_graph.restype = vp
+    lib.mb2_build_launch_graph_all.argtypes = [vp]
+    lib.mb2_build_launch_graph_all.restype = vp
+    lib.mb2_build_render_graph.argtypes = [vp]
+    lib.mb2_build_render_graph.restype = vp
+    lib.mb2_launch_graph_destroy.argtypes = [vp]
+    lib.mb2_launch_graph_destroy.restype = None
+    lib.mb2_run.argtypes = [vp, vp]
+    lib.mb2_run.restype = ctypes.c_int
+    lib.mb2_run_async.argtypes = [vp, vp, vp]
+    lib.mb2_run_async.restype = ctypes.c_int
+    lib.mb2_get_exported.argtypes = [vp, ctypes.c_int64]
+    lib.mb2_get_exported.restype = vp
+    lib.mb2_last_error.argtypes = []
+    lib.mb2_last_error.restype = ctypes.c_char_p
+    lib.mb2_get_exported_num_rows.argtypes = [vp, ctypes.c_int64]
+    lib.mb2_get_exported_num_rows.restype = ctypes.c_int64
+    lib.mb2_get_exported_row_bytes.argtypes = [vp, ctypes.c_int64]
+    lib.mb2_get_exported_row_bytes.restype = ctypes.c_int64
+    lib.mb2_launch_graph_num_kernels.argtypes = [vp]
+    lib.mb2_launch_graph_num_kernels.restype = ctypes.c_int64
+    lib.mb2_executor_stream.argtypes = [vp]
+    lib.mb2_executor_stream.restype = vp
+    lib.mb2_jit_precompile.argtypes = [ctypes.POINTER(_CompileConfigC)]
+    lib.mb2_jit_precompile.restype = ctypes.c_int
+    lib.mb2_version.argtypes = []
+    lib.mb2_version.restype = ctypes.c_char_p
+    _LIB = lib
+    return lib
+
+
+def _last_error(lib) -> str:
+    msg = lib.mb2_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+@dataclass
+class StateConfig:
+    """== madrona::StateConfig (mw_gpu.hpp:25-51).  worldInit / userConfig are
+    bytes-like host buffers (numpy arrays or bytes)."""
+    worldInit: bytes
+    numWorldInitBytes: int
+    userConfig: bytes
+    numWorldDataBytes: int
+    worldDataAlignment: int
+    numWorlds: int
+    numTaskGraphs: int
+    numExportedBuffers: int
+
+
+@dataclass
+class CompileConfig:
+    """== madrona::CompileConfig (mw_gpu.hpp:53-73)."""
+    userSources: Sequence[str]
+    userCompileFlags: Sequence[str] = field(default_factory=list)
+    optMode: int = 1   # LTO
+
+    def _to_c(self):
+        srcs = (ctypes.c_char_p * max(len(self.userSources), 1))(
+            *[os.fspath(s).encode() for s in self.userSources])
+        flags = (ctypes.c_char_p * max(len(self.userCompileFlags), 1))(
+            *[f.encode() for f in self.userCompileFlags])
+        c = _CompileConfigC(srcs, len(self.userSources), flags,
+                            len(self.userCompileFlags), self.optMode)
+        return c, (srcs, flags)
+
+
+def precompile(compile_cfg: CompileConfig) -> None:
+    """JIT the simulator for sm_100a into the in-tree kernel cache (no GPU needed)."""
+    lib = load_library()
+    c, keep = compile_cfg._to_c()
+    if lib.mb2_jit_precompile(ctypes.byref(c)) != 0:
+        raise MadronaB200Error(_last_error(lib))
+    del keep
+
+
+def _as_bytes(buf) -> bytes:
+    if buf is None:
+        return b""
+    if isinstance(buf, (bytes, bytearray)):
+        return bytes(buf)
+    return bytes(memoryview(buf).cast("B"))
+
+
+class MWCudaLaunchGraph:
+    def __init__(self, lib, handle, owner):
+        self._lib = lib
+        self._h = handle
+        self._owner = owner   # keep the executor alive
+
+    @property
+    def num_kernels(self) -> int:
+        return int(self._lib.mb2_launch_graph_num_kernels(self._h))
+
+    def __del__(self):
+        try:
+            if self._h and self._owner._h:
+                self._lib.mb2_launch_graph_destroy(self._h)
+        except Exception:
+            pass
+        self._h = None
+
+
+class _CudaView:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr,
+            "data": (int(ptr), False), "version": 2, "strides": None,
+        }
+
+
+_TYPESTR = {"float32": "<f4", "int32": "<i4", "uint32": "<u4", "uint8": "|u1",
+            "int64": "<i8", "float64": "<f8", "int8": "|i1", "int16": "<i2", "uint16": "<u2"}
+
+
+class MWCudaExecutor:
+    """Mirror of madrona::MWCudaExecutor (mw_gpu.hpp:118-164)."""
+
+    @staticmethod
+    def initCUDA(gpu_id: int) -> int:
+        lib = load_library()
+        if lib.mb2_init_cuda(gpu_id) != 0:
+            raise MadronaB200Error(_last_error(lib))
+        return gpu_id
+
+    def __init__(self, state_cfg: StateConfig, compile_cfg: CompileConfig,
+                 gpu_id: int = 0, render_cfg=None):
+        self._lib = load_library()
+        self._h = None
+        self.gpu_id = gpu_id
+        self.num_worlds = state_cfg.numWorlds
+        init = _as_bytes(state_cfg.worldInit)
+        if len(init) != state_cfg.numWorldInitBytes * state_cfg.numWorlds:
+            raise MadronaB200Error("worldInit must hold numWorlds * numWorldInitBytes bytes")
+        ucfg = _as_bytes(state_cfg.userConfig)
+        init_buf = ctypes.create_string_buffer(init, max(len(init), 1))
+        ucfg_buf = ctypes.create_string_buffer(ucfg, max(len(ucfg), 1))
+        sc = _StateConfigC(
+            ctypes.cast(init_buf, ctypes.c_void_p), state_cfg.numWorldInitBytes,
+            ctypes.cast(ucfg_buf, ctypes.c_void_p), len(ucfg),
+            state_cfg.numWorldDataBytes, state_cfg.worldDataAlignment,
+            state_cfg.numWorlds, state_cfg.numTaskGraphs, state_cfg.numExportedBuffers)
+        cc, keep = compile_cfg._to_c()
+        rc = ctypes.byref(render_cfg) if render_cfg is not None else None
+        h = self._lib.mb2_executor_create(ctypes.byref(sc), ctypes.byref(cc), gpu_id, rc)
+        del keep
+        if not h:
+            raise MadronaB200Error(_last_error(self._lib))
+        self._h = h
+
+    # -- reference API ---------------------------------------------------
+    def buildLaunchGraph(self, taskgraph_ids, stat_name: Optional[str] = None):
+        if isinstance(taskgraph_ids, int):
+            taskgraph_ids = [taskgraph_ids]
+        ids = (ctypes.c_uint32 * len(taskgraph_ids))(*[int(i) for i in taskgraph_ids])
+        g = self._lib.mb2_build_launch_graph(
+            self._h, ids, len(taskgraph_ids), stat_name.encode() if stat_name else None)
+        if not g:
+            raise MadronaB200Error(_last_error(self._lib))
+        return MWCudaLaunchGraph(self._lib, g, self)
+
+    def buildLaunchGraphAllTaskGraphs(self):
+        g = self._lib.mb2_build_launch_graph_all(self._h)
+        if not g:
+            raise MadronaB200Error(_last_error(self._lib))
+        return MWCudaLaunchGraph(self._lib, g, self)
+
+    def buildRenderGraph(self):
+        g = self._lib.mb2_build_render_graph(self._h)
+        if not g:
+            raise MadronaB200Error(_last_error(self._lib))
+        return MWCudaLaunchGraph(self._lib, g, self)
+
+    def run(self, graph: MWCudaLaunchGraph) -> None:
+        if self._lib.mb2_run(self._h, graph._h) != 0:
+            raise MadronaB200Error(_last_error(self._lib))
+
+    def runAsync(self, graph: MWCudaLaunchGraph, stream) -> None:
+        s = getattr(stream, "cuda_stream", stream)
+        if self._lib.mb2_run_async(self._h, graph._h, ctypes.c_void_p(int(s))) != 0:
+            raise MadronaB200Error(_last_error(self._lib))
+
+    def getExported(self, slot: int) -> int:
+        p = self._lib.mb2_get_exported(self._h, int(slot))
+        if not p:
+            raise MadronaB200Error(f"export slot {slot} is empty")
+        return int(p)
+
+    # -- helpers (the role of madrona::py::Tensor, include/madrona/py/utils.hpp:73-141)
+    def exportedNumRows(self, slot: int) -> int:
+        return int(self._lib.mb2_get_exported_num_rows(self._h, int(slot)))
+
+    def exportedRowBytes(self, slot: int) -> int:
+        return int(self._lib.mb2_get_exported_row_bytes(self._h, int(slot)))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.mb2_executor_stream(self._h) or 0)
+
+    def tensor(self, slot: int, dtype: str, shape: Sequence[int]):
+        """Zero-copy torch view of an exported column on this executor's GPU."""
+        import torch
+        view = _CudaView(self.getExported(slot), shape, _TYPESTR[dtype])
+        return torch.as_tensor(view, device=f"cuda:{self.gpu_id}")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.mb2_executor_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
