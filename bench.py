@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- aggregate env-steps/s of the batched ECS step engine.
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+A "step" = one pass of the simulator's step task graph over all worlds
+(MWCudaExecutor::run equivalent).  One process per GPU (torchrun for N>1);
+worlds shard across ranks with no data-path collective, the only exchange is
+the NCCL all_gather of the exported reward/done tensors after each step
+(SURVEY.md 8e).  Prints ONE JSON line on rank 0.
+
+  value     device-timed (CUDA events on the launching stream, max over ranks)
+            throughput with inputs already resident in HBM.
+  e2e       same metric through the C ABI with HOST buffers: every step copies
+            the actions H2D from pinned memory and reads rewards+dones back D2H.
+  roofline  dominant node of the step (per-node CUDA-event timing inside this
+            process via mb2_profile_nodes) vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference
+            the reference's own CPU backend (oracle/_ref, built from the
+            reference sources) running the same fixture on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# workload -> (sim, worlds per GPU, sim cfg, reference-arm worlds (CPU tmp allocator is
+# 32 MiB/world: include/madrona/state.hpp:362, so the CPU arm runs a bounded sample))
+WORKLOADS = {
+    "gridworld": dict(sim="gridworld", worlds=65536,
+                      cfg={"grid_size": 8, "episode_len": 50, "init_items": 12, "seed": 0},
+                      ref_worlds=1024, taskgraphs=[0],
+                      desc="pure-ECS grid sim (BASELINE configs[4] class): 2 agents + <=24 items/world, "
+                           "create/destroy + compaction sort every step"),
+    "cartpole": dict(sim="cartpole", worlds=65536, cfg={"max_steps": 200, "seed": 0},
+                     ref_worlds=1024, taskgraphs=[0],
+                     desc="Cartpole-like fixture (BASELINE configs[0] class)"),
+}
+DEFAULT_WORKLOAD = "gridworld"
+
+try:
+    from bench_workloads import EXTRA_WORKLOADS, EXTRA_DEFAULT  # physics workloads
+    WORKLOADS.update(EXTRA_WORKLOADS)
+    DEFAULT_WORKLOAD = EXTRA_DEFAULT or DEFAULT_WORKLOAD
+except ImportError:
+    pass
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for nm, v in zip(names, parts[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_actions(desc, sim, W, steps, seed):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for s in desc.inputs:
+        if s.name == "reset":
+            out[s.name] = np.zeros((steps, W) + s.per_world, dtype=s.dtype)
+        elif sim == "cartpole":
+            out[s.name] = rng.integers(0, 2, size=(steps, W) + s.per_world).astype(s.dtype)
+        elif sim == "gridworld":
+            out[s.name] = rng.integers(0, 5, size=(steps, W) + s.per_world).astype(s.dtype)
+        else:
+            lo, hi = getattr(s, "range", (0, 4))
+            out[s.name] = rng.integers(lo, hi, size=(steps, W) + s.per_world).astype(s.dtype)
+    return out
+
+
+def run_reference_arm(args, wl):
+    """The reference's own CPU implementation of the path on the host cores."""
+    from oracle import runner
+    from sims import SIMS
+
+    desc = SIMS[wl["sim"]]
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    W = wl["ref_worlds"]
+    steps = args.steps + args.warmup
+    if not runner.available(desc.name):
+        return None
+    t0 = time.time()
+    _, timing = runner.run_reference(desc, W, steps, None, wl["cfg"], workers=cores, want_outputs=False)
+    wall = time.time() - t0
+    return {"value": timing["steps_per_sec"], "unit": "env-steps/s", "cores": cores, "kind": "reference",
+            "sample": f"{desc.name}: {W} worlds x {steps} steps, reference TaskGraphExecutor "
+                      f"numWorkers={cores} (oracle/_ref, g++ -O2 -march=x86-64-v3), zero actions, "
+                      f"{timing['seconds']:.2f}s in run() / {wall:.1f}s wall",
+            "ms_per_step": timing["seconds"] / steps * 1e3, "worlds": W}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (default: workload's)")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.worlds:
+        wl["worlds"] = args.worlds
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+
+    metric = "aggregate env-steps/sec"
+    config = {"workload": f"{args.workload}: {wl['desc']}", "worlds_per_gpu": wl["worlds"],
+              "sim_cfg": wl["cfg"], "parallelism": f"world-shard x{world_size}"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = run_reference_arm(args, wl)
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
+            return
+        line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "env-steps/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+                "config": dict(config, worlds_per_gpu=res["worlds"]),
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from sims import SIMS, make_executor
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    desc = SIMS[wl["sim"]]
+    W = wl["worlds"]
+    cfg = dict(wl["cfg"])
+    cfg["seed"] = int(cfg.get("seed", 0)) + rank * W       # disjoint worlds per rank
+    ex = make_executor(wl["sim"], W, gpu_id=local_rank, **cfg)
+    graph = ex.buildLaunchGraph(wl["taskgraphs"])
+    launches_per_step = graph.num_kernels
+
+    in_t = {s.name: ex.tensor(s.slot, s.dtype, (W,) + s.per_world) for s in desc.inputs}
+    fixed_out = [s for s in desc.outputs if not s.dynamic and s.name in ("reward", "done")]
+    out_t = {s.name: ex.tensor(s.slot, s.dtype, (W,) + s.per_world) for s in fixed_out}
+    gathered = {k: torch.empty((world_size,) + tuple(v.shape), dtype=v.dtype, device=dev)
+                for k, v in out_t.items()} if world_size > 1 else {}
+
+    n_act = 16
+    host_actions = make_actions(desc, wl["sim"], W, n_act, seed=1000 + rank)
+    dev_actions = {k: torch.from_numpy(v).to(dev) for k, v in host_actions.items()}
+    pinned_actions = {k: torch.from_numpy(v).pin_memory() for k, v in host_actions.items()}
+    pinned_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out_t.items()}
+
+    stream = torch.cuda.current_stream()
+    flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one_step(i, host_io=False):
+        if host_io:
+            for k, t in in_t.items():
+                t.copy_(pinned_actions[k][i % n_act], non_blocking=True)
+        else:
+            for k, t in in_t.items():
+                t.copy_(dev_actions[k][i % n_act], non_blocking=True)
+        ex.runAsync(graph, stream)
+        if world_size > 1:
+            for k, t in out_t.items():
+                dist.all_gather_into_tensor(gathered[k], t)
+        if host_io:
+            for k, t in out_t.items():
+                pinned_out[k].copy_(t, non_blocking=True)
+
+    def timed(host_io):
+        for i in range(args.warmup):
+            one_step(i, host_io)
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            if flush is not None:
+                flush.fill_(i & 0xff)
+            starts[i].record(stream)
+            one_step(i, host_io)
+            ends[i].record(stream)
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    total_ms = timed(host_io=False)
+    e2e_ms = timed(host_io=True)
+    clocks = sampler.stop() if sampler else None
+
+    h2d = sum(int(np.prod(v.shape[1:])) * v.dtype.itemsize for v in host_actions.values())
+    d2h = sum(t.numel() * t.element_size() for t in out_t.values())
+
+    roofline = None
+    cpu_base = None
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        prof = ex.profileNodes(wl["taskgraphs"], reps=20)
+        prof = [p for p in prof if p["bytes"] > 0 and p["ms"] > 0]
+        if prof:
+            top = max(prof, key=lambda p: p["ms"])
+            gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": top["kind"], "node": top["node"],
+                        "achieved": gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                        "frac": gbs / peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": top["bytes"], "ms_per_launch": top["ms"],
+                        "rows": top["rows"],
+                        "all_nodes": [{"kind": p["kind"], "ms": round(p["ms"], 5),
+                                       "gbs": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1)} for p in prof]}
+        if world_size == 1 and not args.no_cpu_baseline:
+            small = argparse.Namespace(steps=min(args.steps, 200), warmup=min(args.warmup, 10))
+            res = run_reference_arm(small, wl)
+            if res:
+                cpu_base = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    ex.close()
+    if rank == 0:
+        total_worlds = W * world_size
+        line = {
+            "metric": metric,
+            "value": total_worlds * args.steps / (total_ms * 1e-3),
+            "unit": "env-steps/s",
+            "n_gpus": world_size,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32+i32",
+            "data": "synthetic",
+            "config": dict(config, l2="flushed between steps (256 MiB write)" if flush is not None
+                           else "not flushed"),
+            "clocks": clocks,
+            "e2e": {"value": total_worlds * args.steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_step) * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

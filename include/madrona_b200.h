@@ -134,6 +134,18 @@ void *mb2_executor_stream(mb2_executor *exec);
  * Returns 0 on success. */
 int mb2_jit_precompile(const mb2_compile_config *compile_cfg);
 
+/* Per-node device timing (CUDA events on the executor's stream) of the task
+ * graphs in taskgraph_ids, averaged over `reps` steps; this ADVANCES the
+ * simulation by `reps` steps.  Replaces the reference's device tracing
+ * (src/mw/device/include/madrona/mw_gpu/tracing.hpp, scripts/
+ * parse_device_tracing.py).  Writes a JSON array of
+ * {"node","kind","archetype","launches","ms","rows","bytes"} into json_out
+ * ("bytes" = algorithmic bytes per launch).  Returns the number
+ * of characters needed (excluding NUL), or -1 on error. */
+int64_t mb2_profile_nodes(mb2_executor *exec, const uint32_t *taskgraph_ids,
+                          uint32_t num_taskgraphs, uint32_t reps,
+                          char *json_out, uint64_t json_capacity);
+
 /* Version string. */
 const char *mb2_version(void);
 

@@ -542,11 +542,146 @@ static LaunchGraph *buildGraph(Executor *ex, const uint32_t *ids, uint32_t n, co
     return g;
 }
 
+// ---- per-node profiling ------------------------------------------------------
+
+struct NodeProfile {
+    double ms = 0;
+    double bytes = 0;
+    double rows = 0;
+    int64_t launches = 0;
+    int64_t samples = 0;
+};
+
+static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint32_t reps,
+                            std::string *out)
+{
+    EngineState &S = *ex->hState;
+    cudaSetDevice(ex->gpu);
+    std::vector<uint32_t> order;
+    for (uint32_t i = 0; i < n; i++) {
+        if (ids[i] >= S.numTaskGraphs) {
+            setError("taskgraph id out of range");
+            return -1;
+        }
+        for (uint32_t node = 0; node < S.numNodes; node++) {
+            if (S.nodes[node].taskgraph == ids[i]) order.push_back(node);
+        }
+    }
+    std::vector<NodeProfile> prof(order.size());
+    std::vector<cudaEvent_t> ev(order.size() + 1);
+    for (auto &e : ev) cudaEventCreate(&e);
+    std::vector<TableDesc> tables(S.numArchetypes);
+
+    for (uint32_t rep = 0; rep < reps + 1; rep++) {   // rep 0 = warm-up
+        // snapshot row counts / dirty flags as they are at the start of the step
+        cudaStreamSynchronize(ex->stream);
+        cudaMemcpy(tables.data(), ex->dState->tables, sizeof(TableDesc) * S.numArchetypes,
+                   cudaMemcpyDeviceToHost);
+        cudaEventRecord(ev[0], ex->stream);
+        for (size_t k = 0; k < order.size(); k++) {
+            if (!enqueueNode(ex, order[k], ex->stream)) return -1;
+            cudaEventRecord(ev[k + 1], ex->stream);
+        }
+        if (cudaStreamSynchronize(ex->stream) != cudaSuccess) {
+            setError(std::string("profile step failed: ") + cudaGetErrorString(cudaGetLastError()));
+            return -1;
+        }
+        if (rep == 0) continue;
+        for (size_t k = 0; k < order.size(); k++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+            const NodeRecord &r = S.nodes[order[k]];
+            NodeProfile &p = prof[k];
+            p.ms += ms;
+            p.samples++;
+            const TableDesc &t = tables[r.archetype < S.numArchetypes ? r.archetype : 0];
+            double rows = t.numRows, bytes = 0;
+            if (r.kind == NodeUserParallelFor) {
+                double per_row = 4;   // WorldID
+                for (int c = 0; c < r.numCols; c++) per_row += t.columnBytes[r.cols[c]];
+                bytes = rows * per_row;
+            } else if (r.kind == NodeSortArchetype || r.kind == NodeCompactArchetype) {
+                int col = r.kind == NodeSortArchetype ? S.columnLookup[r.archetype][r.component] : 1;
+                bool active = col != 1 || t.needsSort;
+                if (active) {
+                    // 4 (histogram) + 16 P (key+idx in/out per pass) +
+                    // 4 (idx read) + sum 2 b_c (payload once in, once out) + 8 (remap + offsets)
+                    double per_row = 4 + 16.0 * sortNumPasses(ex, col) + 4 + 8;
+                    for (int c = 0; c < t.numColumns; c++) {
+                        if (c != col) per_row += 2.0 * t.columnBytes[c];
+                    }
+                    bytes = rows * per_row;
+                } else {
+                    rows = 0;
+                }
+            } else if (r.kind >= NodePhysBroadphaseUpdate) {
+                const char *nm;
+                int64_t prow = 0;
+                bytes = (double)physicsNodeBytes(ex, r, &nm, &prow);
+                rows = (double)prow;
+            }
+            p.bytes += bytes;
+            p.rows += rows;
+        }
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+
+    static const char *kind_names[] = { "parallel_for", "sort_archetype", "compact_archetype",
+                                        "clear_tmp", "reset_tmp_alloc", "recycle_entities" };
+    std::string js = "[";
+    for (size_t k = 0; k < order.size(); k++) {
+        const NodeRecord &r = S.nodes[order[k]];
+        const NodeProfile &p = prof[k];
+        const char *kn = r.kind < 6 ? kind_names[r.kind] : "physics";
+        if (r.kind >= NodePhysBroadphaseUpdate) {
+            int64_t rows;
+            physicsNodeBytes(ex, r, &kn, &rows);
+        }
+        std::string name = kn;
+        if (r.kind == NodeUserParallelFor && r.kernelID < ex->jit.nodeKernels.size()) {
+            // keep the mangled system name readable: take the part after "_Z" of the NTTP
+            const std::string &m = ex->jit.nodeKernels[r.kernelID];
+            size_t a = m.find("XadL_Z");
+            if (a != std::string::npos) {
+                size_t b = m.find("ERS", a);
+                name += ":" + m.substr(a + 6, b == std::string::npos ? 32 : b - a - 6);
+            }
+        }
+        double s = p.samples ? 1.0 / (double)p.samples : 0.0;
+        char buf[512];
+        snprintf(buf, sizeof(buf),
+                 "%s{\"node\": %u, \"kind\": \"%s\", \"archetype\": %u, \"ms\": %.6f, "
+                 "\"rows\": %.1f, \"bytes\": %.1f}",
+                 k ? ", " : "", order[k], name.c_str(), r.archetype, p.ms * s, p.rows * s, p.bytes * s);
+        js += buf;
+    }
+    js += "]";
+    *out = js;
+    return (int64_t)js.size();
+}
+
 }
 
 using namespace mb2;
 
 extern "C" {
+
+int64_t mb2_profile_nodes(mb2_executor *exec, const uint32_t *taskgraph_ids,
+                          uint32_t num_taskgraphs, uint32_t reps,
+                          char *json_out, uint64_t json_capacity)
+{
+    g_last_error.clear();
+    std::string js;
+    int64_t n = profileNodes((Executor *)exec, taskgraph_ids, num_taskgraphs, reps, &js);
+    if (n < 0) return -1;
+    if (json_out && json_capacity > 0) {
+        size_t c = std::min<size_t>(js.size(), json_capacity - 1);
+        memcpy(json_out, js.data(), c);
+        json_out[c] = 0;
+    }
+    return n;
+}
+
 
 const char *mb2_last_error(void) { return g_last_error.c_str(); }
 

@@ -63,5 +63,6 @@ void sortScratchDestroy(Executor *ex);
 // Stable sort of `archetype` by the low bits of column `col`; col==1 (WorldID)
 // additionally drops rows with key -1 and rebuilds worldOffsets/worldCounts.
 void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStream_t s);
+int sortNumPasses(Executor *ex, int32_t col);
 
 }

@@ -11,6 +11,12 @@ bool physicsEnqueueNode(Executor *, const NodeRecord &rec, cudaStream_t, std::st
     *err = "physics node kind " + std::to_string(rec.kind) + " not available in this build";
     return false;
 }
+uint64_t physicsNodeBytes(Executor *, const NodeRecord &, const char **name, int64_t *rows)
+{
+    *name = "physics";
+    *rows = 0;
+    return 0;
+}
 LaunchGraph *physicsBuildRenderGraph(Executor *, std::string *err)
 {
     *err = "batch ray-cast renderer not available in this build";

@@ -497,6 +497,11 @@ static int worldSortPasses(uint32_t num_worlds)
     return passes < 1 ? 1 : passes;
 }
 
+int sortNumPasses(Executor *ex, int32_t col)
+{
+    return col == 1 ? worldSortPasses(ex->hState->numWorlds) : 4;
+}
+
 void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStream_t s)
 {
     EngineState &S = *ex->hState;

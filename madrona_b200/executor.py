@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "mb2_launch_graph_num_kernels",
     "mb2_executor_stream",
     "mb2_jit_precompile",
+    "mb2_profile_nodes",
     "mb2_version",
 ]
 
@@ -131,6 +132,9 @@ def load_library() -> ctypes.CDLL:
     lib.mb2_executor_stream.restype = vp
     lib.mb2_jit_precompile.argtypes = [ctypes.POINTER(_CompileConfigC)]
     lib.mb2_jit_precompile.restype = ctypes.c_int
+    lib.mb2_profile_nodes.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32,
+                                      ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64]
+    lib.mb2_profile_nodes.restype = ctypes.c_int64
     lib.mb2_version.argtypes = []
     lib.mb2_version.restype = ctypes.c_char_p
     _LIB = lib
@@ -237,6 +241,7 @@ class MWCudaExecutor:
         self._h = None
         self.gpu_id = gpu_id
         self.num_worlds = state_cfg.numWorlds
+        self.num_taskgraphs = state_cfg.numTaskGraphs
         init = _as_bytes(state_cfg.worldInit)
         if len(init) != state_cfg.numWorldInitBytes * state_cfg.numWorlds:
             raise MadronaB200Error("worldInit must hold numWorlds * numWorldInitBytes bytes")
@@ -300,6 +305,18 @@ class MWCudaExecutor:
 
     def exportedRowBytes(self, slot: int) -> int:
         return int(self._lib.mb2_get_exported_row_bytes(self._h, int(slot)))
+
+    def profileNodes(self, taskgraph_ids=None, reps: int = 10):
+        """Per-node device time + algorithmic bytes; advances the sim by `reps` steps."""
+        import json
+        if taskgraph_ids is None:
+            taskgraph_ids = list(range(self.num_taskgraphs))
+        ids = (ctypes.c_uint32 * len(taskgraph_ids))(*[int(i) for i in taskgraph_ids])
+        buf = ctypes.create_string_buffer(1 << 20)
+        n = self._lib.mb2_profile_nodes(self._h, ids, len(taskgraph_ids), reps, buf, len(buf))
+        if n < 0:
+            raise MadronaB200Error(_last_error(self._lib))
+        return json.loads(buf.value.decode())
 
     @property
     def stream(self) -> int:

@@ -28,7 +28,8 @@ def run_reference(desc, num_worlds: int, num_steps: int, inputs: Optional[Dict[s
                   cfg: Dict, workers: int = 1, want_outputs: bool = True, timeout: float = 600.0):
     """inputs[name]: array [steps, worlds, *per_world].  Returns (outputs, timing)
     where outputs[name] has shape [steps + 1, worlds, *per_world] (index 0 =
-    state right after construction)."""
+    state right after construction); dynamic-table slots are lists of
+    [rows_t, *per_row] arrays instead."""
     exe = binary(desc.name)
     if not os.path.exists(exe):
         raise FileNotFoundError(f"{exe} missing: run `make -C oracle` where /root/reference exists")
@@ -71,5 +72,8 @@ def run_reference(desc, num_worlds: int, num_steps: int, inputs: Optional[Dict[s
                     frame[slot.name] = arr.reshape((-1,) + slot.per_world)
                 frames.append(frame)
             for slot in desc.outputs:
-                outputs[slot.name] = np.stack([f[slot.name] for f in frames])
+                if slot.dynamic:
+                    outputs[slot.name] = [f[slot.name] for f in frames]
+                else:
+                    outputs[slot.name] = np.stack([f[slot.name] for f in frames])
     return outputs, timing

@@ -15,7 +15,8 @@ class Slot:
     slot: int
     name: str
     dtype: str                 # numpy dtype name
-    per_world: Tuple[int, ...]  # shape of one world's rows (fixed tables)
+    per_world: Tuple[int, ...]  # shape of one world's rows (fixed tables) / of one row (dynamic)
+    dynamic: bool = False      # rows = live rows of a dynamic table (varies per step)
 
 
 @dataclass
@@ -43,7 +44,33 @@ def _cartpole_init(w, cfg):
     return struct.pack("<I", int(cfg.get("seed", 0)) + w)
 
 
+def _grid_cfg(cfg):
+    return struct.pack("<iii", int(cfg["grid_size"]), int(cfg["episode_len"]), int(cfg["init_items"]))
+
+
+def _grid_init(w, cfg):
+    return struct.pack("<I", int(cfg.get("seed", 0)) + w)
+
+
 SIMS: Dict[str, SimDesc] = {
+    "gridworld": SimDesc(
+        name="gridworld",
+        sources=[os.path.join(_ROOT, "gridworld", "sim.cpp")],
+        num_exports=10,
+        num_taskgraphs=1,
+        inputs=[Slot(0, "reset", "int32", (1,)), Slot(1, "action", "int32", (2,))],
+        outputs=[Slot(2, "agent_pos", "int32", (2, 2)), Slot(3, "reward", "float32", (2,)),
+                 Slot(4, "obs", "int32", (2, 4)), Slot(5, "item_count", "int32", (1,)),
+                 Slot(9, "done", "int32", (1,)),
+                 Slot(6, "item_pos", "int32", (2,), dynamic=True),
+                 Slot(7, "item_entity", "int32", (2,), dynamic=True),
+                 Slot(8, "item_kind", "int32", (1,), dynamic=True)],
+        pack_config=_grid_cfg,
+        pack_init=_grid_init,
+        oracle_extra=lambda cfg: [int(cfg["grid_size"]), int(cfg["episode_len"]),
+                                  int(cfg["init_items"]), int(cfg.get("seed", 0))],
+        defaults={"grid_size": 8, "episode_len": 50, "init_items": 6, "seed": 0},
+    ),
     "cartpole": SimDesc(
         name="cartpole",
         sources=[os.path.join(_ROOT, "cartpole", "sim.cpp")],

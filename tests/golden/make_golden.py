@@ -15,12 +15,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle.runner import run_reference  # noqa: E402
 from sims import SIMS  # noqa: E402
-from trace_utils import make_inputs, golden_path  # noqa: E402
+from trace_utils import make_inputs, save_golden  # noqa: E402
 
 CASES = [
     # (file, sim, worlds, steps, cfg)
     ("cartpole_w64_s300", "cartpole", 64, 300, {"max_steps": 200, "seed": 0}),
     ("cartpole_w3_s50", "cartpole", 3, 50, {"max_steps": 10, "seed": 7}),
+    ("gridworld_w32_s150", "gridworld", 32, 150,
+     {"grid_size": 6, "episode_len": 40, "init_items": 6, "seed": 11}),
+    # tiny grid + long episodes: many pickups, item table saturates at kMaxItems
+    ("gridworld_w5_s400", "gridworld", 5, 400,
+     {"grid_size": 3, "episode_len": 97, "init_items": 20, "seed": 3}),
 ]
 
 if __name__ == "__main__":
@@ -30,8 +35,6 @@ if __name__ == "__main__":
             continue
         inputs = make_inputs(sim, W, steps, seed=1234)
         outs, _ = run_reference(SIMS[sim], W, steps, inputs, cfg, workers=1)
-        payload = {"in_" + k: v for k, v in inputs.items()}
-        payload.update({"out_" + k: v for k, v in outs.items()})
-        payload["meta"] = np.array([W, steps], dtype=np.int64)
-        np.savez_compressed(golden_path(name), **payload)
-        print(name, {k: v.shape for k, v in outs.items()})
+        save_golden(name, inputs, outs, W, steps)
+        print(name, {k: (v.shape if not isinstance(v, list) else f"{len(v)} frames")
+                     for k, v in outs.items()})

@@ -7,15 +7,7 @@ import pytest
 
 from oracle import runner
 from sims import SIMS
-from trace_utils import golden_path, make_inputs, rollout_gpu
-
-
-def _load(name):
-    z = np.load(golden_path(name))
-    ins = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
-    outs = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
-    W, steps = (int(v) for v in z["meta"])
-    return W, steps, ins, outs
+from trace_utils import load_golden as _load, make_inputs, rollout_gpu
 
 
 @pytest.mark.skipif(not runner.available("cartpole"), reason="oracle/_ref not built")
