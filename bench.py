@@ -119,9 +119,13 @@ def make_actions(desc, sim, W, steps, seed):
             out[s.name] = rng.integers(0, 2, size=(steps, W) + s.per_world).astype(s.dtype)
         elif sim == "gridworld":
             out[s.name] = rng.integers(0, 5, size=(steps, W) + s.per_world).astype(s.dtype)
+        elif sim == "room":
+            amount = rng.integers(0, 4, size=(steps, W, 2))
+            angle = rng.integers(0, 8, size=(steps, W, 2))
+            rot = rng.integers(0, 5, size=(steps, W, 2))
+            out[s.name] = np.stack([amount, angle, rot], axis=-1).astype(s.dtype)
         else:
-            lo, hi = getattr(s, "range", (0, 4))
-            out[s.name] = rng.integers(lo, hi, size=(steps, W) + s.per_world).astype(s.dtype)
+            out[s.name] = rng.integers(0, 4, size=(steps, W) + s.per_world).astype(s.dtype)
     return out
 
 

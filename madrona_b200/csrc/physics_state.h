@@ -1,0 +1,129 @@
+// physics_state.h -- layouts shared by the NVRTC-side physics API
+// (device/madrona/physics.hpp: what simulator code calls) and the ahead-of-time
+// physics kernels (kernels_physics.cu).  Plain structs, no std headers.
+//
+// The public component structs (Velocity, CollisionPrimitive, ObjectManager,
+// RigidBodyMetadata, HalfEdgeMesh ...) keep the reference's field order and
+// sizes (include/madrona/physics.hpp:12-153, geo.hpp:7-45) so a simulator's
+// ObjectManager blob is interchangeable between the reference CPU backend and
+// this engine.  Engine-internal state (candidate / contact buffers, per-world
+// BVH storage) is laid out for the GPU instead of being ECS archetypes.
+#pragma once
+
+#include "mb2_state.h"
+
+namespace mb2 {
+
+struct PVec3 { float x, y, z; };
+struct PQuat { float w, x, y, z; };
+struct PAABB { PVec3 pMin, pMax; };
+
+// == broadphase::BVH::Node (include/madrona/broadphase.hpp:62-78): 4-wide node,
+// child boxes in SoA, leaf children tagged with bit 31, sentinel = -1.
+struct BVHNode {
+    float minX[4];
+    float minY[4];
+    float minZ[4];
+    float maxX[4];
+    float maxY[4];
+    float maxZ[4];
+    i32 children[4];
+    i32 parentID;
+};
+
+struct LeafTransform {
+    PVec3 pos;
+    PQuat rot;
+    PVec3 scale;
+};
+
+// One per world: the payload of the broadphase::BVH singleton component.
+struct WorldBVH {
+    BVHNode *nodes;
+    u64 *leafEntities;        // Entity {gen,id} packed as in the table column
+    const void *objMgr;       // const phys::ObjectManager *
+    i32 *leafObjIDs;
+    PAABB *leafAABBs;
+    LeafTransform *leafTransforms;
+    u32 *leafParents;         // (node << 2) | child
+    i32 *sortedLeaves;
+    i32 numNodes;
+    i32 numAllocatedNodes;
+    i32 numLeaves;
+    i32 numAllocatedLeaves;
+    float velExpansion;
+    float accelExpansion;
+    i32 forceRebuild;
+    i32 pad;
+};
+
+// == phys::PhysicsSystemState (src/physics/physics_impl.hpp:7-15)
+struct PhysicsWorldParams {
+    float deltaT;
+    float h;
+    PVec3 g;
+    float gMagnitude;
+    float restitutionThreshold;
+    u32 contactArchetypeID;
+    u32 jointArchetypeID;
+};
+
+// == phys::CandidateCollision (physics.hpp:52-57)
+struct Candidate {
+    u32 aArch; i32 aRow;
+    u32 bArch; i32 bRow;
+    u32 aPrim;
+    u32 bPrim;
+};
+
+// == phys::ContactConstraint (physics.hpp:59-65) + xpbd::XPBDContactState
+struct Contact {
+    u32 refArch; i32 refRow;
+    u32 altArch; i32 altRow;
+    float points[4][4];       // xyz + penetration depth
+    i32 numPoints;
+    PVec3 normal;
+    float lambdaN[4];
+};
+
+enum PhysCol : int {
+    PCPosition = 0, PCRotation, PCScale, PCObjectID, PCResponseType, PCLeafID,
+    PCVelocity, PCExtForce, PCExtTorque, PCPrevState, PCPreSolvePos, PCPreSolveVel,
+    PCCount
+};
+
+constexpr int kMaxBodyArchetypes = 16;
+constexpr int kMaxHullVerts = 16;     // narrowphase per-thread staging caps
+constexpr int kMaxHullFaces = 16;
+constexpr int kMaxFaceVerts = 8;
+
+struct BodyArchetype {
+    u32 archetype;
+    i32 cols[PCCount];
+};
+
+struct PhysicsState {
+    // ---- written by the device-side PhysicsSystem::registerTypes (1 thread)
+    u32 registered;
+    u32 solver;
+    u32 componentIDs[PCCount];
+    u32 cidJointConstraint;
+    u32 bvhArchetype;            // singleton archetypes
+    u32 paramsArchetype;
+    u32 objectDataArchetype;
+    u32 jointArchetype;
+
+    // ---- filled by the host after registerTypes
+    u32 numBodyArchetypes;
+    BodyArchetype bodies[kMaxBodyArchetypes];   // ascending archetype id
+    i32 jointCol;
+
+    Candidate *candidates;       // [numWorlds][maxCandidatesPerWorld]
+    i32 *candCounts;             // [numWorlds]
+    i32 maxCandidatesPerWorld;
+    Contact *contacts;           // [numWorlds][maxContactsPerWorld]
+    i32 *contactCounts;
+    i32 maxContactsPerWorld;
+};
+
+}

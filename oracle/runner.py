@@ -40,6 +40,12 @@ def run_reference(desc, num_worlds: int, num_steps: int, inputs: Optional[Dict[s
                 "--workers", str(workers)]
         for i, v in enumerate(desc.oracle_extra(full)):
             args += [f"--x{i}", str(v)]
+        if getattr(desc, "objects", None) is not None:
+            from sims.objects import write_blob_file
+            blob, relocs = desc.objects()
+            obj_path = os.path.join(tmp, "objects.bin")
+            write_blob_file(obj_path, blob, relocs)
+            args += ["--objects", obj_path]
         if inputs is not None:
             in_path = os.path.join(tmp, "in.bin")
             with open(in_path, "wb") as f:

@@ -34,6 +34,8 @@ class SimDesc:
     # extra args for the oracle harness (--x0 .. --x3)
     oracle_extra: Callable[[Dict], List[int]]
     defaults: Dict = field(default_factory=dict)
+    # () -> (blob, relocs): ObjectManager blob whose address goes into Config
+    objects: Callable = None
 
 
 def _cartpole_cfg(cfg):
@@ -52,7 +54,40 @@ def _grid_init(w, cfg):
     return struct.pack("<I", int(cfg.get("seed", 0)) + w)
 
 
+def _room_cfg(cfg):
+    return struct.pack("<QII", int(cfg.get("obj_mgr_ptr", 0)), int(cfg["episode_len"]), 0)
+
+
+def _room_init(w, cfg):
+    return struct.pack("<I", int(cfg.get("seed", 0)) + w)
+
+
+def _room_objects():
+    from .objects import room_objects
+    return room_objects()
+
+
 SIMS: Dict[str, SimDesc] = {
+    "room": SimDesc(
+        name="room",
+        sources=[os.path.join(_ROOT, "room", "sim.cpp")],
+        num_exports=13,
+        num_taskgraphs=1,
+        inputs=[Slot(0, "reset", "int32", (1,)), Slot(1, "action", "int32", (2, 3))],
+        outputs=[Slot(2, "reward", "float32", (2,)), Slot(3, "done", "int32", (2,)),
+                 Slot(4, "self_obs", "float32", (2, 9)), Slot(5, "lidar", "float32", (2, 16, 2)),
+                 Slot(6, "agent_pos", "float32", (2, 3)), Slot(7, "agent_rot", "float32", (2, 4)),
+                 Slot(8, "body_count", "int32", (1,)),
+                 Slot(9, "body_pos", "float32", (3,), dynamic=True),
+                 Slot(10, "body_rot", "float32", (4,), dynamic=True),
+                 Slot(11, "body_entity", "int32", (2,), dynamic=True),
+                 Slot(12, "body_vel", "float32", (6,), dynamic=True)],
+        pack_config=_room_cfg,
+        pack_init=_room_init,
+        oracle_extra=lambda cfg: [int(cfg["episode_len"]), int(cfg.get("seed", 0))],
+        defaults={"episode_len": 100, "seed": 0},
+        objects=_room_objects,
+    ),
     "gridworld": SimDesc(
         name="gridworld",
         sources=[os.path.join(_ROOT, "gridworld", "sim.cpp")],
@@ -98,6 +133,21 @@ def make_executor(name: str, num_worlds: int, gpu_id: int = 0, **cfg):
     desc = SIMS[name]
     full = dict(desc.defaults)
     full.update(cfg)
+    keep_alive = None
+    if desc.objects is not None:
+        # upload the ObjectManager blob and relocate its pointers to device addresses
+        import numpy as np
+        import torch
+        from .objects import relocate
+        blob, relocs = desc.objects()
+        dev_buf = torch.empty(len(blob) + 64, dtype=torch.uint8, device=f"cuda:{gpu_id}")
+        base = (dev_buf.data_ptr() + 63) // 64 * 64
+        fixed = relocate(blob, relocs, base)
+        start = base - dev_buf.data_ptr()
+        dev_buf[start:start + len(fixed)].copy_(torch.from_numpy(np.frombuffer(fixed, dtype=np.uint8).copy()))
+        torch.cuda.synchronize(gpu_id)
+        full["obj_mgr_ptr"] = base
+        keep_alive = dev_buf
     inits = pack_world_inits(desc, num_worlds, full)
     state = mb.StateConfig(
         worldInit=inits,
@@ -111,4 +161,6 @@ def make_executor(name: str, num_worlds: int, gpu_id: int = 0, **cfg):
     )
     compile_cfg = mb.CompileConfig(userSources=desc.sources,
                                    userCompileFlags=["-I" + os.path.dirname(desc.sources[0])])
-    return mb.MWCudaExecutor(state, compile_cfg, gpu_id=gpu_id)
+    ex = mb.MWCudaExecutor(state, compile_cfg, gpu_id=gpu_id)
+    ex._keep_alive = keep_alive
+    return ex

@@ -1,0 +1,169 @@
+"""Collision-object description for the rigid-body fixtures: builds the
+madrona::phys::ObjectManager (include/madrona/physics.hpp:145-153 -- same
+layout in this engine's device/madrona/physics.hpp) as ONE relocatable blob:
+all arrays in a single buffer, pointer fields stored as offsets plus a
+relocation list.  The oracle harness relocates it to host addresses, the GPU
+path to device addresses, so both backends read identical geometry.
+
+The reference builds this through PhysicsLoader + convex-hull processing
+(src/physics/physics_assets.cpp, out of scope: SURVEY.md 8f N2); fixtures
+hand-build boxes and a plane instead.
+"""
+from __future__ import annotations
+
+import struct
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+TYPE_SPHERE, TYPE_HULL, TYPE_PLANE = 1, 2, 4
+
+
+def box_half_edge_mesh():
+    """Unit cube [-0.5, 0.5]^3 as a half-edge mesh; twins are (2k, 2k+1)."""
+    v = np.array([[x, y, z] for z in (-0.5, 0.5) for y in (-0.5, 0.5) for x in (-0.5, 0.5)],
+                 dtype=np.float32)
+    # CCW loops seen from outside
+    faces = [
+        [0, 2, 3, 1],   # -z
+        [4, 5, 7, 6],   # +z
+        [0, 1, 5, 4],   # -y
+        [2, 6, 7, 3],   # +y
+        [0, 4, 6, 2],   # -x
+        [1, 3, 7, 5],   # +x
+    ]
+    return build_half_edge_mesh(v, faces)
+
+
+def build_half_edge_mesh(verts: np.ndarray, faces: Sequence[Sequence[int]]):
+    edge_ids = {}
+    hedges: List[List[int]] = []          # [next, rootVertex, face], index = half-edge id
+    face_base = []
+    directed = {}
+    for f, loop in enumerate(faces):
+        n = len(loop)
+        for i in range(n):
+            a, b = loop[i], loop[(i + 1) % n]
+            key = (min(a, b), max(a, b))
+            if key not in edge_ids:
+                edge_ids[key] = len(edge_ids)
+                he = 2 * edge_ids[key]
+            else:
+                he = 2 * edge_ids[key] + 1
+            assert (a, b) not in directed, "non-manifold"
+            directed[(a, b)] = he
+    n_he = 2 * len(edge_ids)
+    hedges = [[0, 0, 0] for _ in range(n_he)]
+    for f, loop in enumerate(faces):
+        n = len(loop)
+        ids = [directed[(loop[i], loop[(i + 1) % n])] for i in range(n)]
+        face_base.append(ids[0])
+        for i in range(n):
+            hedges[ids[i]] = [ids[(i + 1) % n], loop[i], f]
+    planes = []
+    for loop in faces:
+        p0, p1, p2 = verts[loop[0]], verts[loop[1]], verts[loop[2]]
+        nrm = np.cross(p1 - p0, p2 - p0).astype(np.float64)
+        nrm /= np.linalg.norm(nrm)
+        nrm = nrm.astype(np.float32)
+        planes.append([nrm[0], nrm[1], nrm[2], np.float32(np.dot(nrm, p0))])
+    return dict(vertices=np.asarray(verts, dtype=np.float32),
+                half_edges=np.asarray(hedges, dtype=np.uint32),
+                face_base=np.asarray(face_base, dtype=np.uint32),
+                planes=np.asarray(planes, dtype=np.float32))
+
+
+class BlobBuilder:
+    def __init__(self):
+        self.buf = bytearray()
+        self.relocs: List[int] = []
+
+    def align(self, a: int):
+        while len(self.buf) % a:
+            self.buf.append(0)
+
+    def add(self, data: bytes, align: int = 16) -> int:
+        self.align(align)
+        off = len(self.buf)
+        self.buf += data
+        return off
+
+    def pointer_at(self, where: int, target_offset: int):
+        struct.pack_into("<Q", self.buf, where, target_offset)
+        self.relocs.append(where)
+
+
+def _metadata(inv_mass, inv_inertia, mu_s, mu_d) -> bytes:
+    # RigidBodyMassData {invMass, invInertiaTensor[3], toCenterOfMass[3], toInteriaFrame(w,x,y,z)}
+    # + RigidBodyFrictionData {muS, muD}  = 52 bytes
+    return struct.pack("<f3f3f4f2f", inv_mass, *inv_inertia, 0, 0, 0, 1, 0, 0, 0, mu_s, mu_d)
+
+
+def room_objects() -> Tuple[bytes, List[int]]:
+    """Objects of sims/room: 0 Cube, 1 Wall, 2 Agent, 3 Plane (one primitive each)."""
+    mesh = box_half_edge_mesh()
+    b = BlobBuilder()
+    mgr_off = b.add(b"\0" * 48)
+
+    he_off = b.add(mesh["half_edges"].tobytes())
+    fb_off = b.add(mesh["face_base"].tobytes())
+    pl_off = b.add(mesh["planes"].tobytes())
+    vt_off = b.add(mesh["vertices"].tobytes())
+
+    n_obj = 4
+    prim_size = 56
+    prims_off = b.add(b"\0" * (prim_size * n_obj), align=16)
+    for i, ty in enumerate([TYPE_HULL, TYPE_HULL, TYPE_HULL, TYPE_PLANE]):
+        base = prims_off + i * prim_size
+        struct.pack_into("<I", b.buf, base, ty)
+        if ty == TYPE_HULL:
+            b.pointer_at(base + 8, he_off)
+            b.pointer_at(base + 16, fb_off)
+            b.pointer_at(base + 24, pl_off)
+            b.pointer_at(base + 32, vt_off)
+            struct.pack_into("<III", b.buf, base + 40, len(mesh["half_edges"]),
+                             len(mesh["planes"]), len(mesh["vertices"]))
+
+    hull_aabb = struct.pack("<6f", -0.5, -0.5, -0.5, 0.5, 0.5, 0.5)
+    big = 1.0e5
+    plane_aabb = struct.pack("<6f", -big, -big, -big, big, big, 0.0)
+    aabbs = hull_aabb * 3 + plane_aabb
+    prim_aabb_off = b.add(aabbs)
+    body_aabb_off = b.add(aabbs)
+    offs_off = b.add(np.arange(n_obj, dtype=np.uint32).tobytes())
+    cnts_off = b.add(np.ones(n_obj, dtype=np.uint32).tobytes())
+
+    def box_inv_inertia(mass, sx, sy, sz):
+        ix = mass / 12.0 * (sy * sy + sz * sz)
+        iy = mass / 12.0 * (sx * sx + sz * sz)
+        iz = mass / 12.0 * (sx * sx + sy * sy)
+        return [np.float32(1.0 / ix), np.float32(1.0 / iy), np.float32(1.0 / iz)]
+
+    cube_m, agent_m = 10.0, 50.0
+    meta = b""
+    meta += _metadata(np.float32(1.0 / cube_m), box_inv_inertia(cube_m, 1.5, 1.5, 1.5), 0.5, 0.75)
+    meta += _metadata(0.0, [0.0, 0.0, 0.0], 0.5, 0.5)                      # wall (static)
+    agent_inv_i = box_inv_inertia(agent_m, 1.0, 1.0, 1.5)
+    meta += _metadata(np.float32(1.0 / agent_m), [0.0, 0.0, agent_inv_i[2]], 0.5, 0.5)  # yaw only
+    meta += _metadata(0.0, [0.0, 0.0, 0.0], 0.5, 0.5)                      # plane
+    meta_off = b.add(meta)
+
+    for i, target in enumerate([prims_off, prim_aabb_off, body_aabb_off, offs_off, cnts_off, meta_off]):
+        b.pointer_at(mgr_off + 8 * i, target)
+    return bytes(b.buf), b.relocs
+
+
+def relocate(blob: bytes, relocs: Sequence[int], base_address: int) -> bytes:
+    out = bytearray(blob)
+    for where in relocs:
+        (off,) = struct.unpack_from("<Q", out, where)
+        struct.pack_into("<Q", out, where, base_address + off)
+    return bytes(out)
+
+
+def write_blob_file(path: str, blob: bytes, relocs: Sequence[int]) -> None:
+    """u64 size, u64 numRelocs, relocs[], blob (read by oracle/harness_room.cpp)."""
+    with open(path, "wb") as f:
+        f.write(struct.pack("<QQ", len(blob), len(relocs)))
+        f.write(np.asarray(relocs, dtype=np.uint64).tobytes())
+        f.write(blob)

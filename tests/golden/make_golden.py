@@ -26,6 +26,8 @@ CASES = [
     # tiny grid + long episodes: many pickups, item table saturates at kMaxItems
     ("gridworld_w5_s400", "gridworld", 5, 400,
      {"grid_size": 3, "episode_len": 97, "init_items": 20, "seed": 3}),
+    # rigid-body room: two resets inside the trace (episode_len 100 + random resets)
+    ("room_w4_s210", "room", 4, 210, {"episode_len": 100, "seed": 21}),
 ]
 
 if __name__ == "__main__":

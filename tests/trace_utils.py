@@ -24,6 +24,18 @@ def make_inputs(sim: str, num_worlds: int, num_steps: int, seed: int = 0) -> Dic
             "reset": (rng.random((num_steps, num_worlds, 1)) < 0.02).astype(np.int32),
             "action": rng.integers(0, 5, size=(num_steps, num_worlds, 2), dtype=np.int32),
         }
+    if sim == "room":
+        # mostly "full speed ahead" so agents reach cubes, walls and each other
+        amount = np.where(rng.random((num_steps, num_worlds, 2)) < 0.7, 3,
+                          rng.integers(0, 4, size=(num_steps, num_worlds, 2)))
+        angle = np.where(rng.random((num_steps, num_worlds, 2)) < 0.7, 0,
+                         rng.integers(0, 8, size=(num_steps, num_worlds, 2)))
+        act = np.stack([amount, angle,
+                        rng.integers(0, 5, size=(num_steps, num_worlds, 2))], axis=-1)
+        return {
+            "reset": (rng.random((num_steps, num_worlds, 1)) < 0.005).astype(np.int32),
+            "action": act.astype(np.int32),
+        }
     raise KeyError(sim)
 
 
