@@ -512,6 +512,20 @@ static LaunchGraph *buildGraph(Executor *ex, const uint32_t *ids, uint32_t n, co
         }
         for (uint32_t node = 0; node < S.numNodes && ok; node++) {
             if (S.nodes[node].taskgraph != ids[i]) continue;
+            if (S.nodes[node].kind >= NodePhysBroadphaseUpdate && S.nodes[node].kind < NodeRenderPrepare) {
+                // a run of consecutive physics nodes is one fused launch
+                uint32_t last = node;
+                while (last + 1 < S.numNodes && S.nodes[last + 1].taskgraph == ids[i] &&
+                       S.nodes[last + 1].kind >= NodePhysBroadphaseUpdate &&
+                       S.nodes[last + 1].kind < NodeRenderPrepare) {
+                    last++;
+                }
+                std::string perr;
+                ok = physicsEnqueueNodes(ex, &S.nodes[node], last - node + 1, ex->stream, &perr);
+                if (!ok) setError(perr);
+                node = last;
+                continue;
+            }
             ok = enqueueNode(ex, node, ex->stream);
         }
     }

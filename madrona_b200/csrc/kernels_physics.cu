@@ -135,10 +135,9 @@ struct BodyView {
 
 __device__ __forceinline__ const BodyArchetype *bodyOf(const PhysicsState &P, u32 arch)
 {
-    for (u32 i = 0; i < P.numBodyArchetypes; i++) {
-        if (P.bodies[i].archetype == arch) return &P.bodies[i];
-    }
-    return nullptr;
+    if (arch >= (u32)kMaxArchetypes) return nullptr;
+    const int idx = P.bodyIndex[arch];
+    return idx < 0 ? nullptr : &P.bodies[idx];
 }
 
 template <typename T>
@@ -218,20 +217,9 @@ __device__ __forceinline__ AABB growByMotion(AABB box, Vector3 v, float vel_k, f
     return box;
 }
 
-__global__ void __launch_bounds__(256)
-physUpdateLeavesKernel(EngineState *Sp)
+__device__ __forceinline__ void rowUpdateLeaf(const EngineState &S, const PhysicsState &P, const BodyArchetype &b, const i32 row, const i32 w)
 {
-    const EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    if (blockIdx.y >= P.numBodyArchetypes) return;
-    const BodyArchetype &b = P.bodies[blockIdx.y];
-    const TableDesc &t = S.tables[b.archetype];
-    const i32 n = t.numRows;
-    const i32 *world_col = (const i32 *)t.columns[1];
-
-    for (i32 row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-        const i32 w = world_col[row];
-        if (w < 0) continue;
+    {
         WorldBVH &bvh = worldBVH(S, P, w);
         const PObjectManager &objs = *(const PObjectManager *)bvh.objMgr;
 
@@ -381,13 +369,9 @@ __device__ void rebuildWorldBVH(WorldBVH &bvh)
     }
 }
 
-__global__ void __launch_bounds__(128)
-physRebuildBVHKernel(EngineState *Sp)
+__device__ __forceinline__ void phaseRebuild(const EngineState &S, const PhysicsState &P, const i32 w, const int lane)
 {
-    const EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    const i32 w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= (i32)S.numWorlds) return;
+    if (lane != 0) return;
     WorldBVH &bvh = worldBVH(S, P, w);
     if (!bvh.forceRebuild) return;
     bvh.forceRebuild = 0;
@@ -436,21 +420,9 @@ __device__ void refitLeaf(WorldBVH &bvh, i32 leaf)
     }
 }
 
-__global__ void __launch_bounds__(256)
-physRefitKernel(EngineState *Sp)
+__device__ __forceinline__ void rowRefit(const EngineState &S, const PhysicsState &P, const BodyArchetype &b, const i32 row, const i32 w)
 {
-    const EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    if (blockIdx.y >= P.numBodyArchetypes) return;
-    const BodyArchetype &b = P.bodies[blockIdx.y];
-    const TableDesc &t = S.tables[b.archetype];
-    const i32 n = t.numRows;
-    const i32 *world_col = (const i32 *)t.columns[1];
-    for (i32 row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-        const i32 w = world_col[row];
-        if (w < 0) continue;
-        refitLeaf(worldBVH(S, P, w), bodyCol<i32>(S, b, PCLeafID, row));
-    }
+    refitLeaf(worldBVH(S, P, w), bodyCol<i32>(S, b, PCLeafID, row));
 }
 
 // ---- candidate pairs: one warp per world, CPU iteration order -----------------------------
@@ -504,15 +476,8 @@ __device__ __forceinline__ void forEachPartner(const WorldBVH &bvh, const PairVi
     }
 }
 
-__global__ void __launch_bounds__(128)
-physFindCandidatesKernel(EngineState *Sp)
+__device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const i32 w, const int lane)
 {
-    EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    const int lane = threadIdx.x & 31;
-    const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (w >= (i32)S.numWorlds) return;
-
     const WorldBVH &bvh = worldBVH(S, P, w);
     const PObjectManager &objs = *(const PObjectManager *)bvh.objMgr;
     Candidate *out = P.candidates + (size_t)w * P.maxCandidatesPerWorld;
@@ -525,7 +490,7 @@ physFindCandidatesKernel(EngineState *Sp)
         const i32 count = t.worldCounts[w];
         for (i32 base = 0; base < count; base += 32) {
             const i32 row = first + base + lane;
-            const bool valid = base + lane < count;
+            const bool valid = base + lane < count && ((const i32 *)t.columns[1])[row] == w;
 
             PairVisitor v { S, P, objs, 0, false, 0 };
             AABB box = AABB::invalid();
@@ -538,10 +503,22 @@ physFindCandidatesKernel(EngineState *Sp)
                 box = AABB { { lb.pMin.x, lb.pMin.y, lb.pMin.z }, { lb.pMax.x, lb.pMax.y, lb.pMax.z } };
             }
 
-            // pass 1: how many candidates does this row emit
+            // one traversal: remember the partners (in traversal order), count
+            // the candidates they stand for
+            constexpr int kKeep = 12;
+            u32 keep_arch[kKeep];
+            i32 keep_row[kKeep];
+            u32 keep_prims[kKeep];
+            int partners = 0;
             i32 mine = 0;
             if (valid) {
-                forEachPartner(bvh, v, box, [&](u32, i32, u32 b_prims) {
+                forEachPartner(bvh, v, box, [&](u32 b_arch, i32 b_row, u32 b_prims) {
+                    if (partners < kKeep) {
+                        keep_arch[partners] = b_arch;
+                        keep_row[partners] = b_row;
+                        keep_prims[partners] = b_prims;
+                    }
+                    partners++;
                     mine += (i32)(v.selfPrims * b_prims);
                 });
             }
@@ -554,18 +531,22 @@ physFindCandidatesKernel(EngineState *Sp)
             const i32 total = __shfl_sync(0xffffffffu, incl, 31);
             i32 at = running + incl - mine;
 
-            // pass 2: same traversal, now writing
-            if (valid && mine > 0) {
-                forEachPartner(bvh, v, box, [&](u32 b_arch, i32 b_row, u32 b_prims) {
-                    const u32 checks = v.selfPrims * b_prims;
-                    for (u32 c = 0; c < checks; c++) {
-                        if (at < P.maxCandidatesPerWorld) {
-                            out[at] = Candidate { b.archetype, row, b_arch, b_row,
-                                                  c / b_prims, c % b_prims };
-                        }
-                        at++;
+            auto emit = [&](u32 b_arch, i32 b_row, u32 b_prims) {
+                const u32 checks = v.selfPrims * b_prims;
+                for (u32 c = 0; c < checks; c++) {
+                    if (at < P.maxCandidatesPerWorld) {
+                        out[at] = Candidate { b.archetype, row, b_arch, b_row,
+                                              c / b_prims, c % b_prims };
                     }
-                });
+                    at++;
+                }
+            };
+            if (valid && mine > 0) {
+                if (partners <= kKeep) {
+                    for (int k = 0; k < partners; k++) emit(keep_arch[k], keep_row[k], keep_prims[k]);
+                } else {
+                    forEachPartner(bvh, v, box, emit);   // rare: more partners than kept
+                }
             }
             running += total;
         }
@@ -583,20 +564,9 @@ physFindCandidatesKernel(EngineState *Sp)
 // Integration (xpbd.cpp:100-185) and velocity update (xpbd.cpp:738-779)
 // =============================================================================================
 
-__global__ void __launch_bounds__(256)
-physSubstepKernel(EngineState *Sp)
+__device__ __forceinline__ void rowIntegrate(const EngineState &S, const PhysicsState &P, const BodyArchetype &b, const i32 row, const i32 w)
 {
-    const EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    if (blockIdx.y >= P.numBodyArchetypes) return;
-    const BodyArchetype &b = P.bodies[blockIdx.y];
-    const TableDesc &t = S.tables[b.archetype];
-    const i32 n = t.numRows;
-    const i32 *world_col = (const i32 *)t.columns[1];
-
-    for (i32 row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-        const i32 w = world_col[row];
-        if (w < 0) continue;
+    {
 
         Vector3 x = bodyCol<Vector3>(S, b, PCPosition, row);
         Quat q = bodyCol<Quat>(S, b, PCRotation, row);
@@ -616,7 +586,7 @@ physSubstepKernel(EngineState *Sp)
             pre_pos.q = q;
             pre_vel.linear = Vector3::zero();
             pre_vel.angular = Vector3::zero();
-            continue;
+            return;
         }
 
         const PhysicsWorldParams &params = worldParams(S, P, w);
@@ -657,20 +627,9 @@ physSubstepKernel(EngineState *Sp)
     }
 }
 
-__global__ void __launch_bounds__(256)
-physSetVelocitiesKernel(EngineState *Sp)
+__device__ __forceinline__ void rowSetVelocity(const EngineState &S, const PhysicsState &P, const BodyArchetype &b, const i32 row, const i32 w)
 {
-    const EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    if (blockIdx.y >= P.numBodyArchetypes) return;
-    const BodyArchetype &b = P.bodies[blockIdx.y];
-    const TableDesc &t = S.tables[b.archetype];
-    const i32 n = t.numRows;
-    const i32 *world_col = (const i32 *)t.columns[1];
-
-    for (i32 row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-        const i32 w = world_col[row];
-        if (w < 0) continue;
+    {
         const float h = worldParams(S, P, w).h;
         const Vector3 x = bodyCol<Vector3>(S, b, PCPosition, row);
         const Quat q = bodyCol<Quat>(S, b, PCRotation, row);
@@ -1071,7 +1030,8 @@ __device__ __forceinline__ void writeContact(Contact &c, u32 ref_arch, i32 ref_r
     }
     c.numPoints = m.count;
     c.normal = PVec3 { m.normal.x, m.normal.y, m.normal.z };
-    for (int i = 0; i < 4; i++) c.lambdaN[i] = 0.f;
+    for (int i = 0; i < 3; i++) c.lambdaN[i] = 0.f;
+    c.level = 0;
 }
 
 __device__ __forceinline__ ManifoldOut singlePoint(Vector3 p, Vector3 n, float depth)
@@ -1088,164 +1048,413 @@ __device__ __forceinline__ ManifoldOut singlePoint(Vector3 p, Vector3 n, float d
     return m;
 }
 
-// One candidate -> at most one contact (narrowphase.cpp:1682-1899 + 1516-1680).
-__device__ bool narrowphaseOne(EngineState &S, const PhysicsState &P, const PObjectManager &objs,
-                               const Candidate &cand, Contact &out)
+// ---- one candidate -> at most one contact (narrowphase.cpp:1682-1899 + 1516-1680) ------
+//
+// Stage A (every lane, its own candidate): order the pair by primitive type,
+// fetch both transforms, primitive-AABB reject, and finish the cheap pair
+// types (sphere-sphere, sphere-plane, hull-plane) on the spot.
+// Stage B (whole warp, one hull-hull candidate at a time): both hulls are
+// transformed into shared memory by all lanes, the 2 x F face queries and the
+// E_a x E_b edge query are spread over the lanes, and the winner is picked with
+// the reference's sequential rule (first strictly-greater separation in index
+// order, stop at the first positive one) -- expressed as "lowest index among
+// positives, else lowest index among maxima", which is order independent and
+// therefore bit-identical.  Only the final clipping runs on the owning lane.
+
+struct PairSetup {
+    u32 aArch, bArch;
+    i32 aRow, bRow;
+    const PCollisionPrimitive *aPrim, *bPrim;
+    Vector3 aPos, bPos;
+    Quat aRot, bRot;
+    Diag3x3 aScale, bScale;
+    u32 test;          // 0 = rejected
+};
+
+__device__ __forceinline__ PairSetup setupPair(const EngineState &S, const PhysicsState &P,
+                                               const PObjectManager &objs, const Candidate &cand)
 {
-    u32 a_arch = cand.aArch, b_arch = cand.bArch;
-    i32 a_row = cand.aRow, b_row = cand.bRow;
-    u32 a_prim_idx = objs.primOffsets[locCol<i32>(S, P, a_arch, a_row, PCObjectID)] + cand.aPrim;
-    u32 b_prim_idx = objs.primOffsets[locCol<i32>(S, P, b_arch, b_row, PCObjectID)] + cand.bPrim;
-    const PCollisionPrimitive *a_prim = &objs.prims[a_prim_idx];
-    const PCollisionPrimitive *b_prim = &objs.prims[b_prim_idx];
-    u32 ta = a_prim->type, tb = b_prim->type;
+    PairSetup ps;
+    ps.aArch = cand.aArch; ps.bArch = cand.bArch;
+    ps.aRow = cand.aRow; ps.bRow = cand.bRow;
+    u32 a_prim_idx = objs.primOffsets[locCol<i32>(S, P, ps.aArch, ps.aRow, PCObjectID)] + cand.aPrim;
+    u32 b_prim_idx = objs.primOffsets[locCol<i32>(S, P, ps.bArch, ps.bRow, PCObjectID)] + cand.bPrim;
+    ps.aPrim = &objs.prims[a_prim_idx];
+    ps.bPrim = &objs.prims[b_prim_idx];
+    u32 ta = ps.aPrim->type, tb = ps.bPrim->type;
     // order the pair by primitive type: sphere(1) < hull(2) < plane(4)
     if (ta > tb) {
         u32 tu;
         i32 ti;
         const PCollisionPrimitive *tp;
-        tu = a_arch; a_arch = b_arch; b_arch = tu;
-        ti = a_row; a_row = b_row; b_row = ti;
-        tp = a_prim; a_prim = b_prim; b_prim = tp;
+        tu = ps.aArch; ps.aArch = ps.bArch; ps.bArch = tu;
+        ti = ps.aRow; ps.aRow = ps.bRow; ps.bRow = ti;
+        tp = ps.aPrim; ps.aPrim = ps.bPrim; ps.bPrim = tp;
         tu = a_prim_idx; a_prim_idx = b_prim_idx; b_prim_idx = tu;
         tu = ta; ta = tb; tb = tu;
     }
+    ps.aPos = locCol<Vector3>(S, P, ps.aArch, ps.aRow, PCPosition);
+    ps.bPos = locCol<Vector3>(S, P, ps.bArch, ps.bRow, PCPosition);
+    ps.aRot = locCol<Quat>(S, P, ps.aArch, ps.aRow, PCRotation);
+    ps.bRot = locCol<Quat>(S, P, ps.bArch, ps.bRow, PCRotation);
+    ps.aScale = locCol<Diag3x3>(S, P, ps.aArch, ps.aRow, PCScale);
+    ps.bScale = locCol<Diag3x3>(S, P, ps.bArch, ps.bRow, PCScale);
 
-    const Vector3 a_pos = locCol<Vector3>(S, P, a_arch, a_row, PCPosition);
-    const Vector3 b_pos = locCol<Vector3>(S, P, b_arch, b_row, PCPosition);
-    const Quat a_rot = locCol<Quat>(S, P, a_arch, a_row, PCRotation);
-    const Quat b_rot = locCol<Quat>(S, P, b_arch, b_row, PCRotation);
-    const Diag3x3 a_scale = locCol<Diag3x3>(S, P, a_arch, a_row, PCScale);
-    const Diag3x3 b_scale = locCol<Diag3x3>(S, P, b_arch, b_row, PCScale);
+    AABB a_box = objs.primAABBs[a_prim_idx].applyTRS(ps.aPos, ps.aRot, ps.aScale);
+    AABB b_box = objs.primAABBs[b_prim_idx].applyTRS(ps.bPos, ps.bRot, ps.bScale);
+    ps.test = a_box.intersects(b_box) ? (ta | tb) : 0u;
+    return ps;
+}
 
-    {
-        AABB a_box = objs.primAABBs[a_prim_idx].applyTRS(a_pos, a_rot, a_scale);
-        AABB b_box = objs.primAABBs[b_prim_idx].applyTRS(b_pos, b_rot, b_scale);
-        if (!a_box.intersects(b_box)) return false;
-    }
-
-    Vector3 verts[2 * kMaxHullVerts];
-    PPlane planes[2 * kMaxHullFaces];
-    Vector3 clip_a[kClipCap], clip_b[kClipCap];
-
-    const u32 test = ta | tb;
-    switch (test) {
-    case 1: {   // sphere - sphere
-        const float ra = a_scale.d0 * a_prim->sphereRadius;
-        const float rb = b_scale.d0 * b_prim->sphereRadius;
-        const Vector3 to_b = b_pos - a_pos;
+// sphere-sphere (1), sphere-plane (5), hull-plane (6): finished by the lane itself
+__device__ bool narrowphaseSimple(EngineState &S, const PairSetup &ps, Contact &out)
+{
+    switch (ps.test) {
+    case 1: {
+        const float ra = ps.aScale.d0 * ps.aPrim->sphereRadius;
+        const float rb = ps.bScale.d0 * ps.bPrim->sphereRadius;
+        const Vector3 to_b = ps.bPos - ps.aPos;
         const float dist = to_b.length();
         if (dist > ra + rb) return false;
         const Vector3 n = dist > 0.f ? to_b / dist : madrona::math::up;
         // single-point contacts store (ref, alt) = (b, a)
-        writeContact(out, b_arch, b_row, a_arch, a_row,
-                     singlePoint(a_pos + ra * n, n, ra + rb - dist));
+        writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow,
+                     singlePoint(ps.aPos + ra * n, n, ra + rb - dist));
         return true;
     }
-    case 5: {   // sphere - plane
-        const float ra = a_scale.d0 * a_prim->sphereRadius;
-        const Vector3 n = b_rot.rotateVec(Vector3 { 0, 0, 1 });
-        const float d = n.dot(b_pos);
-        const float t = n.dot(a_pos) - d;
+    case 5: {
+        const float ra = ps.aScale.d0 * ps.aPrim->sphereRadius;
+        const Vector3 n = ps.bRot.rotateVec(Vector3 { 0, 0, 1 });
+        const float d = n.dot(ps.bPos);
+        const float t = n.dot(ps.aPos) - d;
         const float pen = ra - t;
         if (pen < 0) return false;
-        writeContact(out, b_arch, b_row, a_arch, a_row, singlePoint(a_pos - t * n, n, pen));
+        writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, singlePoint(ps.aPos - t * n, n, pen));
         return true;
     }
-    case 2: {   // hull - hull
-        const PHalfEdgeMesh &am = a_prim->hull;
-        const PHalfEdgeMesh &bm = b_prim->hull;
-        if (am.numVertices > (u32)kMaxHullVerts || bm.numVertices > (u32)kMaxHullVerts ||
-                am.numFaces > (u32)kMaxHullFaces || bm.numFaces > (u32)kMaxHullFaces) {
-            atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
-            return false;
-        }
-        HullInWorld a = placeHull(am, a_pos, a_rot, a_scale, verts, planes);
-        HullInWorld b = placeHull(bm, b_pos, b_rot, b_scale, verts + kMaxHullVerts, planes + kMaxHullFaces);
-
-        FaceAxis fa = bestFaceAxis(a, b);
-        if (fa.separation > 0.0f) return false;
-        FaceAxis fb = bestFaceAxis(b, a);
-        if (fb.separation > 0.0f) return false;
-        EdgeAxis e = bestEdgeAxis(a, b);
-        if (e.separation > 0.0f) return false;
-
-        const bool face_a = fa.separation > e.separation;
-        const bool face_b = fb.separation > e.separation;
-        if (face_a || face_b) {
-            const bool a_is_ref = fa.separation >= fb.separation;
-            const PPlane ref_plane = a_is_ref ? fa.plane : fb.plane;
-            const i32 ref_face = a_is_ref ? fa.face : fb.face;
-            const HullInWorld &ref = a_is_ref ? a : b;
-            const HullInWorld &inc = a_is_ref ? b : a;
-            const i32 inc_face = mostOpposedFace(inc, ref_plane.normal);
-            ManifoldOut m = faceFaceManifold(ref_plane, ref_face, inc_face, ref, inc, clip_a, clip_b);
-            if (m.count <= 0) return false;
-            if (a_is_ref) writeContact(out, a_arch, a_row, b_arch, b_row, m);
-            else writeContact(out, b_arch, b_row, a_arch, a_row, m);
-            return true;
-        }
-        // edge - edge: contact point on A's edge, depth = -separation, A is ref
-        const PHalfEdge ha = a.mesh->halfEdges[e.edgeA];
-        const PHalfEdge hb = b.mesh->halfEdges[e.edgeB];
-        const Vector3 p = closestOnFirstSegment(
-            a.verts[ha.rootVertex], a.verts[a.mesh->halfEdges[ha.next].rootVertex],
-            b.verts[hb.rootVertex], b.verts[b.mesh->halfEdges[hb.next].rootVertex]);
-        ManifoldOut m = singlePoint(p, e.normal, -e.separation);
-        writeContact(out, a_arch, a_row, b_arch, b_row, m);
-        return true;
-    }
-    case 6: {   // hull - plane (plane is b and the reference)
-        const PHalfEdgeMesh &am = a_prim->hull;
+    case 6: {   // plane is b and the reference
+        const PHalfEdgeMesh &am = ps.aPrim->hull;
         if (am.numVertices > (u32)kMaxHullVerts || am.numFaces > (u32)kMaxHullFaces) {
             atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
             return false;
         }
-        HullInWorld a = placeHull(am, a_pos, a_rot, a_scale, verts, planes);
-        const Vector3 n = b_rot.rotateVec(Vector3 { 0, 0, 1 });
-        const PPlane plane { n, dot(n, b_pos) };
+        Vector3 verts[kMaxHullVerts];
+        PPlane planes[kMaxHullFaces];
+        Vector3 clip[kClipCap];
+        HullInWorld a = placeHull(am, ps.aPos, ps.aRot, ps.aScale, verts, planes);
+        const Vector3 n = ps.bRot.rotateVec(Vector3 { 0, 0, 1 });
+        const PPlane plane { n, dot(n, ps.bPos) };
         if (hullSupportDistance(plane, a) > 0.0f) return false;
         const i32 inc_face = mostOpposedFace(a, plane.normal);
-        ManifoldOut m = facePlaneManifold(plane, inc_face, a, clip_a);
+        ManifoldOut m = facePlaneManifold(plane, inc_face, a, clip);
         if (m.count <= 0) return false;
-        writeContact(out, b_arch, b_row, a_arch, a_row, m);
+        writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, m);
         return true;
     }
     default:
-        // sphere - hull needs the GJK closest-point routine (geo.cpp:38-59):
-        // not part of this build
+        // sphere - hull needs the GJK closest-point routine (geo.cpp:38-59): not in this build
         atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
         return false;
     }
 }
 
-// one warp per world: candidates in order, contacts compacted in order
-__global__ void __launch_bounds__(64)
-physNarrowphaseKernel(EngineState *Sp)
+struct HullScratch {
+    Vector3 verts[2 * kMaxHullVerts];
+    PPlane planes[2 * kMaxHullFaces];
+    Vector3 clipA[kClipCap];
+    Vector3 clipB[kClipCap];
+};
+
+template <typename T>
+__device__ __forceinline__ T warpBroadcast(T v, int src)
 {
-    EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    const int lane = threadIdx.x & 31;
-    const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (w >= (i32)S.numWorlds) return;
+    static_assert(sizeof(T) % 4 == 0, "");
+    union { T t; u32 w[sizeof(T) / 4]; } in, out;
+    in.t = v;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); i++) out.w[i] = __shfl_sync(0xffffffffu, in.w[i], src);
+    return out.t;
+}
+
+// (separation, index) of the element the sequential scan would have kept.
+__device__ __forceinline__ void warpSequentialWinner(float &sep, i32 &idx, bool have)
+{
+    const u32 positives = __ballot_sync(0xffffffffu, have && sep > 0.f);
+    if (positives) {
+        // lowest index among positives; lanes hold disjoint ascending index sets,
+        // so compare indices explicitly
+        i32 cand = (have && sep > 0.f) ? idx : 0x7fffffff;
+        for (int o = 16; o >= 1; o >>= 1) {
+            i32 other = __shfl_xor_sync(0xffffffffu, cand, o);
+            if (other < cand) cand = other;
+        }
+        const u32 owner = __ballot_sync(0xffffffffu, have && sep > 0.f && idx == cand);
+        const int src = __ffs(owner) - 1;
+        sep = __shfl_sync(0xffffffffu, sep, src);
+        idx = cand;
+        return;
+    }
+    float s = have ? sep : -FLT_MAX;
+    i32 k = have ? idx : 0x7fffffff;
+    for (int o = 16; o >= 1; o >>= 1) {
+        float os = __shfl_xor_sync(0xffffffffu, s, o);
+        i32 ok = __shfl_xor_sync(0xffffffffu, k, o);
+        if (os > s || (os == s && ok < k)) {
+            s = os;
+            k = ok;
+        }
+    }
+    sep = s;
+    idx = k;
+}
+
+// Executed by ALL lanes for the hull-hull candidate owned by lane `src`.
+// Returns (on every lane) whether a contact was produced; the contact itself
+// is valid on lane `src` only.
+__device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const int src, const int lane,
+                                    HullScratch &scratch, Contact &out)
+{
+    const PairSetup ps = warpBroadcast(mine, src);
+    const PHalfEdgeMesh &am = ps.aPrim->hull;
+    const PHalfEdgeMesh &bm = ps.bPrim->hull;
+    const u32 nva = am.numVertices, nvb = bm.numVertices, nfa = am.numFaces, nfb = bm.numFaces;
+    if (nva > (u32)kMaxHullVerts || nvb > (u32)kMaxHullVerts ||
+            nfa > (u32)kMaxHullFaces || nfb > (u32)kMaxHullFaces) {
+        if (lane == src) atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+        return false;
+    }
+
+    // -- both hulls into shared memory (vertex = R S v + t, plane via R S^-1)
+    Vector3 *verts_a = scratch.verts, *verts_b = scratch.verts + kMaxHullVerts;
+    PPlane *planes_a = scratch.planes, *planes_b = scratch.planes + kMaxHullFaces;
+    {
+        const Mat3x3 rot_a = Mat3x3::fromQuat(ps.aRot), rot_b = Mat3x3::fromQuat(ps.bRot);
+        const Mat3x3 vm_a = rot_a * ps.aScale, vm_b = rot_b * ps.bScale;
+        const Mat3x3 nm_a = rot_a * ps.aScale.inv(), nm_b = rot_b * ps.bScale.inv();
+        for (u32 i = lane; i < nva + nvb; i += 32) {
+            if (i < nva) verts_a[i] = vm_a * am.vertices[i] + ps.aPos;
+            else verts_b[i - nva] = vm_b * bm.vertices[i - nva] + ps.bPos;
+        }
+        for (u32 i = lane; i < nfa + nfb; i += 32) {
+            const bool is_a = i < nfa;
+            const PPlane local = is_a ? am.facePlanes[i] : bm.facePlanes[i - nfa];
+            const Mat3x3 &vm = is_a ? vm_a : vm_b;
+            const Mat3x3 &nm = is_a ? nm_a : nm_b;
+            const Vector3 on_plane = vm * (local.normal * local.d) + (is_a ? ps.aPos : ps.bPos);
+            const Vector3 n = (nm * local.normal).normalize();
+            (is_a ? planes_a[i] : planes_b[i - nfa]) = PPlane { n, dot(n, on_plane) };
+        }
+    }
+    __syncwarp();
+    // centres: vertex sums in index order (float addition is not associative)
+    Vector3 center_a = Vector3::zero();
+    for (u32 i = 0; i < nva; i++) center_a += verts_a[i];
+    center_a /= (float)nva;
+
+    HullInWorld a { &am, verts_a, planes_a, nva, nfa, center_a };
+    HullInWorld b { &bm, verts_b, planes_b, nvb, nfb, Vector3::zero() };
+
+    // -- face queries: lane f measures face f (A's faces vs B, then B's vs A)
+    float sep_a = -FLT_MAX, sep_b = -FLT_MAX;
+    i32 face_a = lane, face_b = lane;
+    if ((u32)lane < nfa) sep_a = hullSupportDistance(planes_a[lane], b);
+    warpSequentialWinner(sep_a, face_a, (u32)lane < nfa);
+    if (sep_a > 0.0f) return false;
+    if ((u32)lane < nfb) sep_b = hullSupportDistance(planes_b[lane], a);
+    warpSequentialWinner(sep_b, face_b, (u32)lane < nfb);
+    if (sep_b > 0.0f) return false;
+
+    // -- edge query: pair p = ia * eb + ib, lanes take p = lane, lane + 32, ...
+    const u32 ea = am.numHalfEdges / 2, eb = bm.numHalfEdges / 2;
+    float e_sep = -FLT_MAX;
+    i32 e_pair = 0x7fffffff;
+    Vector3 e_normal = Vector3::zero();
+    for (u32 p = lane; p < ea * eb; p += 32) {
+        const u32 ha = (p / eb) * 2, hb = (p % eb) * 2;
+        const PHalfEdge a0 = am.halfEdges[ha];
+        const PHalfEdge a1 = am.halfEdges[ha ^ 1u];
+        const PHalfEdge b0 = bm.halfEdges[hb];
+        const PHalfEdge b1 = bm.halfEdges[hb ^ 1u];
+        float sep = -FLT_MAX;
+        Vector3 normal = Vector3::zero();
+        if (gaussMapArcsCross(planes_a[a0.face].normal, planes_a[a1.face].normal,
+                              -planes_b[b0.face].normal, -planes_b[b1.face].normal)) {
+            const Vector3 pa = verts_a[a0.rootVertex];
+            const Vector3 qa = verts_a[am.halfEdges[a0.next].rootVertex];
+            const Vector3 pb = verts_b[b0.rootVertex];
+            const Vector3 qb = verts_b[bm.halfEdges[b0.next].rootVertex];
+            const Vector3 axis = (qa - pa).cross(qb - pb);
+            const float len2 = axis.length2();
+            if (len2 != 0) {
+                normal = axis * (1.f / sqrtf(len2));
+                if (normal.dot(pa - center_a) < 0.0f) normal = -normal;
+                sep = normal.dot(pb - pa);
+            }
+        }
+        if (sep > e_sep) {
+            e_sep = sep;
+            e_pair = (i32)p;
+            e_normal = normal;
+            if (sep > 0) break;
+        }
+    }
+    {
+        const float my_sep = e_sep;
+        const i32 my_pair = e_pair;
+        warpSequentialWinner(e_sep, e_pair, my_pair != 0x7fffffff);
+        const u32 owner = __ballot_sync(0xffffffffu, my_pair == e_pair && my_pair != 0x7fffffff &&
+                                                     my_sep == e_sep);
+        if (owner) {
+            e_normal = warpBroadcast(e_normal, __ffs(owner) - 1);
+        } else {
+            // nothing beat the initial -FLT_MAX: the scalar scan keeps its defaults
+            e_sep = -FLT_MAX;
+            e_pair = 0;
+            e_normal = Vector3::zero();
+        }
+    }
+    if (e_sep > 0.0f) return false;
+
+    // -- contact generation on the owning lane (data already in shared memory)
+    bool made = false;
+    if (lane == src) {
+        const bool face_contact_a = sep_a > e_sep;
+        const bool face_contact_b = sep_b > e_sep;
+        if (face_contact_a || face_contact_b) {
+            const bool a_is_ref = sep_a >= sep_b;
+            const PPlane ref_plane = a_is_ref ? planes_a[face_a] : planes_b[face_b];
+            const i32 ref_face = a_is_ref ? face_a : face_b;
+            const HullInWorld &ref = a_is_ref ? a : b;
+            const HullInWorld &inc = a_is_ref ? b : a;
+            const i32 inc_face = mostOpposedFace(inc, ref_plane.normal);
+            ManifoldOut m = faceFaceManifold(ref_plane, ref_face, inc_face, ref, inc,
+                                             scratch.clipA, scratch.clipB);
+            if (m.count > 0) {
+                if (a_is_ref) writeContact(out, ps.aArch, ps.aRow, ps.bArch, ps.bRow, m);
+                else writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, m);
+                made = true;
+            }
+        } else {
+            // edge - edge: contact point on A's edge, depth = -separation, A is ref
+            const u32 ha = ((u32)e_pair / eb) * 2, hb = ((u32)e_pair % eb) * 2;
+            const PHalfEdge he_a = am.halfEdges[ha];
+            const PHalfEdge he_b = bm.halfEdges[hb];
+            const Vector3 p = closestOnFirstSegment(
+                verts_a[he_a.rootVertex], verts_a[am.halfEdges[he_a.next].rootVertex],
+                verts_b[he_b.rootVertex], verts_b[bm.halfEdges[he_b.next].rootVertex]);
+            writeContact(out, ps.aArch, ps.aRow, ps.bArch, ps.bRow, singlePoint(p, e_normal, -e_sep));
+            made = true;
+        }
+    }
+    made = __shfl_sync(0xffffffffu, made ? 1 : 0, src) != 0;
+    __syncwarp();
+    return made;
+}
+
+// A body takes part in contact ordering unless writing it back is a no-op:
+// static (inverse mass / inertia forced to 0, so x is unchanged) AND its
+// rotation is a bitwise fixpoint of normalize() (so q is unchanged).
+__device__ __forceinline__ bool bodyIsMutable(const EngineState &S, const PhysicsState &P, u32 arch, i32 row)
+{
+    if (locCol<u32>(S, P, arch, row, PCResponseType) != kRespStatic) return true;
+    const Quat q = locCol<Quat>(S, P, arch, row, PCRotation);
+    const Quat n = q.normalize();
+    return !(n.w == q.w && n.x == q.x && n.y == q.y && n.z == q.z);
+}
+
+// index of a body inside its world's body list (archetypes ascending, rows in order)
+__device__ __forceinline__ i32 worldBodySlot(const EngineState &S, const PhysicsState &P, i32 w, u32 arch, i32 row)
+{
+    i32 base = 0;
+    for (u32 i = 0; i < P.numBodyArchetypes; i++) {
+        const TableDesc &t = S.tables[P.bodies[i].archetype];
+        if (P.bodies[i].archetype == arch) return base + (row - t.worldOffsets[w]);
+        base += t.worldCounts[w];
+    }
+    return -1;
+}
+
+// one warp per world: candidates in order, contacts compacted in order, then
+// the dependency level of every contact (see Contact::level)
+constexpr int kPhysWarps = 2;     // worlds (warps) per block of the fused physics kernel
+
+struct LevelScratch {
+    i32 lastLevel[kPhysWarps][kMaxLevelBodies];
+    i32 pairInfo[kPhysWarps][32][2];   // body slot * 2 + mutable, per side
+    i32 levelOut[kPhysWarps][32];
+    HullScratch hulls[kPhysWarps];
+};
+
+__device__ void phaseNarrowphase(EngineState &S, const PhysicsState &P, const i32 w, const int lane,
+                                 const int warp, LevelScratch &scratch)
+{
+    i32 (&last_level)[kPhysWarps][kMaxLevelBodies] = scratch.lastLevel;
+    i32 (&pair_info)[kPhysWarps][32][2] = scratch.pairInfo;
+    i32 (&level_out)[kPhysWarps][32] = scratch.levelOut;
+    for (int i = lane; i < kMaxLevelBodies; i += 32) last_level[warp][i] = 0;
+    __syncwarp();
 
     const PObjectManager &objs = worldObjects(S, P, w);
     const Candidate *cands = P.candidates + (size_t)w * P.maxCandidatesPerWorld;
     Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
     const i32 n = P.candCounts[w];
     i32 running = 0;
+    i32 max_level = 0;
+    i32 seq_level = 0;      // fallback when a world has more bodies than the scan tracks
 
     for (i32 base = 0; base < n; base += 32) {
         const i32 i = base + lane;
         Contact c;
         bool hit = false;
-        if (i < n) hit = narrowphaseOne(S, P, objs, cands[i], c);
+        PairSetup ps;
+        ps.test = 0;
+        if (i < n) ps = setupPair(S, P, objs, cands[i]);
+        if (ps.test != 0 && ps.test != 2) hit = narrowphaseSimple(S, ps, c);
+        u32 hull_pairs = __ballot_sync(0xffffffffu, ps.test == 2);
+        while (hull_pairs) {
+            const int src = __ffs(hull_pairs) - 1;
+            hull_pairs &= hull_pairs - 1;
+            const bool made = hullHullCooperative(S, ps, src, lane, scratch.hulls[warp], c);
+            if (lane == src) hit = made;
+        }
         const u32 hits = __ballot_sync(0xffffffffu, hit);
+        const int my_rank = __popc(hits & ((1u << lane) - 1u));
+        const int num_hits = __popc(hits);
         if (hit) {
-            const i32 at = running + __popc(hits & ((1u << lane) - 1u));
+            const i32 s1 = worldBodySlot(S, P, w, c.refArch, c.refRow);
+            const i32 s2 = worldBodySlot(S, P, w, c.altArch, c.altRow);
+            pair_info[warp][my_rank][0] = s1 * 2 + (bodyIsMutable(S, P, c.refArch, c.refRow) ? 1 : 0);
+            pair_info[warp][my_rank][1] = s2 * 2 + (bodyIsMutable(S, P, c.altArch, c.altRow) ? 1 : 0);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int k = 0; k < num_hits; k++) {
+                const i32 a = pair_info[warp][k][0], b = pair_info[warp][k][1];
+                const i32 sa = a >> 1, sb = b >> 1;
+                i32 lvl;
+                if (sa < 0 || sb < 0 || sa >= kMaxLevelBodies || sb >= kMaxLevelBodies) {
+                    lvl = max_level + 1;          // unknown body: strictly after everything so far
+                    seq_level = lvl;
+                } else {
+                    i32 dep = seq_level;
+                    if (a & 1) dep = max(dep, last_level[warp][sa]);
+                    if (b & 1) dep = max(dep, last_level[warp][sb]);
+                    lvl = dep + 1;
+                    if (a & 1) last_level[warp][sa] = lvl;
+                    if (b & 1) last_level[warp][sb] = lvl;
+                }
+                if (lvl > max_level) max_level = lvl;
+                level_out[warp][k] = lvl;
+            }
+        }
+        __syncwarp();
+        if (hit) {
+            const i32 at = running + my_rank;
+            c.level = level_out[warp][my_rank];
             if (at < P.maxContactsPerWorld) contacts[at] = c;
         }
-        running += __popc(hits);
+        running += num_hits;
+        __syncwarp();
     }
     if (lane == 0) {
         if (running > P.maxContactsPerWorld) {
@@ -1253,6 +1462,7 @@ physNarrowphaseKernel(EngineState *Sp)
             running = P.maxContactsPerWorld;
         }
         P.contactCounts[w] = running;
+        P.contactMaxLevel[w] = max_level;
     }
 }
 
@@ -1355,7 +1565,7 @@ __device__ __forceinline__ BodyPair bodyPair(const EngineState &S, const Physics
 __device__ void solveContactPosition(EngineState &S, const PhysicsState &P, const PObjectManager &objs,
                                      Contact &c)
 {
-    for (int i = 0; i < 4; i++) c.lambdaN[i] = 0.f;
+    for (int i = 0; i < 3; i++) c.lambdaN[i] = 0.f;
 
     Vector3 &x1_ref = locCol<Vector3>(S, P, c.refArch, c.refRow, PCPosition);
     Vector3 &x2_ref = locCol<Vector3>(S, P, c.altArch, c.altRow, PCPosition);
@@ -1500,21 +1710,27 @@ __device__ void solveJoint(EngineState &S, const PhysicsState &P, const PObjectM
     q2_ref = q2;
 }
 
-__global__ void __launch_bounds__(128)
-physSolvePositionsKernel(EngineState *Sp)
+// One warp per world.  Contacts are swept level by level (Contact::level): the
+// lanes of a level run concurrently, levels run in order -- same floats as the
+// reference's one-thread-per-world sequential sweep (xpbd.cpp:720-736), a
+// fraction of its latency.  Joints follow sequentially.
+__device__ void phaseSolvePositions(EngineState &S, const PhysicsState &P, const i32 w, const int lane)
 {
-    EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    const i32 w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= (i32)S.numWorlds) return;
     const PObjectManager &objs = worldObjects(S, P, w);
 
     Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
     const i32 n = P.contactCounts[w];
-    for (i32 i = 0; i < n; i++) solveContactPosition(S, P, objs, contacts[i]);
+    const i32 levels = P.contactMaxLevel[w];
+    for (i32 lvl = 1; lvl <= levels; lvl++) {
+        for (i32 base = 0; base < n; base += 32) {
+            const i32 i = base + lane;
+            if (i < n && contacts[i].level == lvl) solveContactPosition(S, P, objs, contacts[i]);
+        }
+        __syncwarp();
+    }
 
     const TableDesc &jt = S.tables[P.jointArchetype];
-    if (jt.numRows > 0) {
+    if (lane == 0 && jt.numRows > 0) {
         const PJoint *joints = (const PJoint *)jt.columns[P.jointCol];
         const i32 *jw = (const i32 *)jt.columns[1];
         const i32 first = jt.worldOffsets[w];
@@ -1627,19 +1843,88 @@ __device__ void solveContactVelocity(EngineState &S, const PhysicsState &P, cons
     vel2_ref = PVelocity { v2, o2 };
 }
 
-__global__ void __launch_bounds__(128)
-physSolveVelocitiesKernel(EngineState *Sp)
+__device__ void phaseSolveVelocities(EngineState &S, const PhysicsState &P, const i32 w, const int lane)
 {
-    EngineState &S = *Sp;
-    const PhysicsState &P = *S.physics;
-    const i32 w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= (i32)S.numWorlds) return;
     const PObjectManager &objs = worldObjects(S, P, w);
     const PhysicsWorldParams &params = worldParams(S, P, w);
     const Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
     const i32 n = P.contactCounts[w];
-    for (i32 i = 0; i < n; i++) {
-        solveContactVelocity(S, P, objs, contacts[i], params.h, params.restitutionThreshold);
+    const i32 levels = P.contactMaxLevel[w];
+    for (i32 lvl = 1; lvl <= levels; lvl++) {
+        for (i32 base = 0; base < n; base += 32) {
+            const i32 i = base + lane;
+            if (i < n && contacts[i].level == lvl) {
+                solveContactVelocity(S, P, objs, contacts[i], params.h, params.restitutionThreshold);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
+// Launchers.  Row-parallel phases (leaf update, refit, integrate, velocity
+// update) are grid-stride kernels over all rows of every body archetype;
+// per-world phases (candidates, narrowphase, solves) give each world a warp.
+// (A single fused warp-per-world kernel for the whole step was measured 2.4x
+// SLOWER on B200: 18.7k SASS instructions with warps spread over every phase
+// thrash the instruction cache, and the light phases inherit the narrowphase's
+// 128-register occupancy.)
+// =============================================================================================
+
+enum PhysPhase : u32 {
+    PhaseUpdateLeaves = 1, PhaseRebuild, PhaseRefit, PhaseFindCandidates, PhaseIntegrate,
+    PhaseNarrowphase, PhaseSolvePositions, PhaseSetVelocities, PhaseSolveVelocities,
+};
+
+template <u32 OP>
+__global__ void __launch_bounds__(256)
+physBodyKernel(EngineState *Sp)
+{
+    const EngineState &S = *Sp;
+    const PhysicsState &P = *S.physics;
+    if (blockIdx.y >= P.numBodyArchetypes) return;
+    const BodyArchetype &b = P.bodies[blockIdx.y];
+    const TableDesc &t = S.tables[b.archetype];
+    const i32 n = t.numRows;
+    const i32 *world_col = (const i32 *)t.columns[1];
+    for (i32 row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        const i32 w = world_col[row];
+        if (w < 0) continue;
+        if constexpr (OP == PhaseUpdateLeaves) rowUpdateLeaf(S, P, b, row, w);
+        else if constexpr (OP == PhaseRefit) rowRefit(S, P, b, row, w);
+        else if constexpr (OP == PhaseIntegrate) rowIntegrate(S, P, b, row, w);
+        else if constexpr (OP == PhaseSetVelocities) rowSetVelocity(S, P, b, row, w);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+physRebuildKernel(EngineState *Sp)
+{
+    const EngineState &S = *Sp;
+    const i32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (i32)S.numWorlds) return;
+    phaseRebuild(S, *S.physics, w, 0);
+}
+
+template <u32 OP>
+__global__ void __launch_bounds__(32 * kPhysWarps, 8)
+physWorldKernel(EngineState *Sp)
+{
+    EngineState &S = *Sp;
+    const PhysicsState &P = *S.physics;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (w >= (i32)S.numWorlds) return;
+    if constexpr (OP == PhaseFindCandidates) {
+        phaseFindCandidates(S, P, w, lane);
+    } else if constexpr (OP == PhaseNarrowphase) {
+        __shared__ LevelScratch scratch;
+        phaseNarrowphase(S, P, w, lane, warp, scratch);
+    } else if constexpr (OP == PhaseSolvePositions) {
+        phaseSolvePositions(S, P, w, lane);
+    } else if constexpr (OP == PhaseSolveVelocities) {
+        phaseSolveVelocities(S, P, w, lane);
     }
 }
 
@@ -1680,6 +1965,7 @@ bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *, std::stri
     // archetypes that carry the whole RigidBody bundle, ascending id == the
     // CPU backend's query iteration order
     P.numBodyArchetypes = 0;
+    memset(P.bodyIndex, 0xff, sizeof(P.bodyIndex));
     for (uint32_t a = 0; a < S.numArchetypes; a++) {
         if (!S.archetypes[a].registered) continue;
         BodyArchetype b;
@@ -1695,6 +1981,7 @@ bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *, std::stri
             *err = "too many rigid-body archetypes";
             return false;
         }
+        P.bodyIndex[a] = (signed char)P.numBodyArchetypes;
         P.bodies[P.numBodyArchetypes++] = b;
     }
     P.jointCol = S.columnLookup[P.jointArchetype][P.cidJointConstraint];
@@ -1711,7 +1998,8 @@ bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *, std::stri
     if (!alloc((void **)&P.candidates, sizeof(Candidate) * W * P.maxCandidatesPerWorld) ||
         !alloc((void **)&P.candCounts, sizeof(i32) * W) ||
         !alloc((void **)&P.contacts, sizeof(Contact) * W * P.maxContactsPerWorld) ||
-        !alloc((void **)&P.contactCounts, sizeof(i32) * W)) {
+        !alloc((void **)&P.contactCounts, sizeof(i32) * W) ||
+        !alloc((void **)&P.contactMaxLevel, sizeof(i32) * W)) {
         *err = "physics buffers allocation failed";
         return false;
     }
@@ -1736,7 +2024,8 @@ static dim3 bodyGrid(Executor *ex)
     return dim3((unsigned)std::max(blocks, 1), std::max(P.numBodyArchetypes, 1u));
 }
 
-bool physicsEnqueueNode(Executor *ex, const NodeRecord &rec, cudaStream_t s, std::string *err)
+bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, cudaStream_t s,
+                         std::string *err)
 {
     PhysicsHost *ph = ex->physics;
     if (!ph || !ph->active) {
@@ -1745,38 +2034,49 @@ bool physicsEnqueueNode(Executor *ex, const NodeRecord &rec, cudaStream_t s, std
     }
     EngineState *d = ex->dState;
     const unsigned W = ex->hState->numWorlds;
+    const unsigned wgrid = (W + kPhysWarps - 1) / kPhysWarps;
+    const unsigned wblock = 32 * kPhysWarps;
     const dim3 bgrid = bodyGrid(ex);
-    switch (rec.kind) {
-    case NodePhysBroadphaseUpdate:
-        physUpdateLeavesKernel<<<bgrid, 256, 0, s>>>(d);
-        if (rec.userTag == 1) physRebuildBVHKernel<<<(W + 127) / 128, 128, 0, s>>>(d);
-        physRefitKernel<<<bgrid, 256, 0, s>>>(d);
-        return true;
-    case NodePhysFindCandidates:
-        // joints are iterated per world by the solver: keep their table in world
-        // order (the reference sorts Joint here too, xpbd.cpp:1092-1096)
-        launchSortArchetype(ex, ph->hPhys.jointArchetype, 1, s);
-        physFindCandidatesKernel<<<(W * 32 + 127) / 128, 128, 0, s>>>(d);
-        return true;
-    case NodePhysSubstepBegin:
-        physSubstepKernel<<<bgrid, 256, 0, s>>>(d);
-        return true;
-    case NodePhysNarrowphase:
-        physNarrowphaseKernel<<<(W * 32 + 63) / 64, 64, 0, s>>>(d);
-        return true;
-    case NodePhysSolvePositions:
-        physSolvePositionsKernel<<<(W + 127) / 128, 128, 0, s>>>(d);
-        return true;
-    case NodePhysSetVelocities:
-        physSetVelocitiesKernel<<<bgrid, 256, 0, s>>>(d);
-        return true;
-    case NodePhysSolveVelocities:
-        physSolveVelocitiesKernel<<<(W + 127) / 128, 128, 0, s>>>(d);
-        return true;
-    default:
-        *err = "unknown physics node kind " + std::to_string(rec.kind);
-        return false;
+    for (uint32_t i = 0; i < count; i++) {
+        const NodeRecord &rec = recs[i];
+        switch (rec.kind) {
+        case NodePhysBroadphaseUpdate:
+            physBodyKernel<PhaseUpdateLeaves><<<bgrid, 256, 0, s>>>(d);
+            if (rec.userTag == 1) physRebuildKernel<<<(W + 127) / 128, 128, 0, s>>>(d);
+            physBodyKernel<PhaseRefit><<<bgrid, 256, 0, s>>>(d);
+            break;
+        case NodePhysFindCandidates:
+            // joints are iterated per world by the solver: keep their table in
+            // world order (the reference sorts Joint here too, xpbd.cpp:1092-1096)
+            launchSortArchetype(ex, ph->hPhys.jointArchetype, 1, s);
+            physWorldKernel<PhaseFindCandidates><<<wgrid, wblock, 0, s>>>(d);
+            break;
+        case NodePhysSubstepBegin:
+            physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
+            break;
+        case NodePhysNarrowphase:
+            physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d);
+            break;
+        case NodePhysSolvePositions:
+            physWorldKernel<PhaseSolvePositions><<<wgrid, wblock, 0, s>>>(d);
+            break;
+        case NodePhysSetVelocities:
+            physBodyKernel<PhaseSetVelocities><<<bgrid, 256, 0, s>>>(d);
+            break;
+        case NodePhysSolveVelocities:
+            physWorldKernel<PhaseSolveVelocities><<<wgrid, wblock, 0, s>>>(d);
+            break;
+        default:
+            *err = "unknown physics node kind " + std::to_string(rec.kind);
+            return false;
+        }
     }
+    return true;
+}
+
+bool physicsEnqueueNode(Executor *ex, const NodeRecord &rec, cudaStream_t s, std::string *err)
+{
+    return physicsEnqueueNodes(ex, &rec, 1, s, err);
 }
 
 uint64_t physicsNodeBytes(Executor *ex, const NodeRecord &rec, const char **name, int64_t *rows)

@@ -10,6 +10,8 @@ bool physicsHostCreate(Executor *ex, std::string *err);
 bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *rc, std::string *err);
 void physicsHostDestroy(Executor *ex);
 bool physicsEnqueueNode(Executor *ex, const NodeRecord &rec, cudaStream_t s, std::string *err);
+bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, cudaStream_t s,
+                         std::string *err);
 LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err);
 // algorithmic bytes of one launch of a physics node + a short name (profiling)
 uint64_t physicsNodeBytes(Executor *ex, const NodeRecord &rec, const char **name, int64_t *rows);

@@ -83,7 +83,12 @@ struct Contact {
     float points[4][4];       // xyz + penetration depth
     i32 numPoints;
     PVec3 normal;
-    float lambdaN[4];
+    float lambdaN[3];         // only [0] is ever read (xpbd.cpp:1028)
+    // Dependency level inside the world's contact list: contacts of one level
+    // touch disjoint (mutable) bodies and every earlier contact they could
+    // depend on has a lower level, so solving level by level in parallel is
+    // bit-identical to the reference's sequential Gauss-Seidel sweep.
+    i32 level;
 };
 
 enum PhysCol : int {
@@ -96,6 +101,7 @@ constexpr int kMaxBodyArchetypes = 16;
 constexpr int kMaxHullVerts = 16;     // narrowphase per-thread staging caps
 constexpr int kMaxHullFaces = 16;
 constexpr int kMaxFaceVerts = 8;
+constexpr int kMaxLevelBodies = 128;  // bodies per world tracked by the contact level scan
 
 struct BodyArchetype {
     u32 archetype;
@@ -116,6 +122,7 @@ struct PhysicsState {
     // ---- filled by the host after registerTypes
     u32 numBodyArchetypes;
     BodyArchetype bodies[kMaxBodyArchetypes];   // ascending archetype id
+    signed char bodyIndex[kMaxArchetypes];      // archetype id -> index into bodies[] or -1
     i32 jointCol;
 
     Candidate *candidates;       // [numWorlds][maxCandidatesPerWorld]
@@ -123,6 +130,7 @@ struct PhysicsState {
     i32 maxCandidatesPerWorld;
     Contact *contacts;           // [numWorlds][maxContactsPerWorld]
     i32 *contactCounts;
+    i32 *contactMaxLevel;        // [numWorlds]
     i32 maxContactsPerWorld;
 };
 

@@ -245,7 +245,16 @@ inline void lidarSystem(Engine &ctx, Entity e, Position &pos, Rotation &rot,
     Quat q = rot;
     Vector3 origin = pos;
     origin.z += 0.25f;
-    for (int32_t i = 0; i < kNumLidar; i++) {
+#ifdef MADRONA_GPU_MODE
+    // GPU backend: the node below runs kNumLidar threads per agent, one ray each
+    // (same pattern as the upstream simulators' warp-level lidar)
+    const int32_t first_ray = (int32_t)(threadIdx.x % kNumLidar);
+    const int32_t last_ray = first_ray + 1;
+#else
+    const int32_t first_ray = 0;
+    const int32_t last_ray = kNumLidar;
+#endif
+    for (int32_t i = first_ray; i < last_ray; i++) {
         Vector3 ray_dir = q.rotateVec(dirs[i]);
         // start just outside the agent's own (rotating) box
         Vector3 ray_o = origin + 0.8f * ray_dir;
@@ -294,8 +303,13 @@ void Sim::setupTasks(TaskGraphManager &mgr, const Config &)
 
     auto obs = builder.addToGraph<ParallelForNode<Engine, observationSystem,
         Position, Rotation, Progress, StepsRemaining, SelfObs>>({post_bvh});
+#ifdef MADRONA_GPU_MODE
+    builder.addToGraph<CustomParallelForNode<Engine, lidarSystem, kNumLidar, 1,
+        Entity, Position, Rotation, Lidar>>({obs});
+#else
     builder.addToGraph<ParallelForNode<Engine, lidarSystem,
         Entity, Position, Rotation, Lidar>>({obs});
+#endif
 }
 
 Sim::Sim(Engine &ctx, const Config &cfg, const WorldInit &init)
