@@ -210,8 +210,11 @@ def main():
 
     desc = SIMS[wl["sim"]]
     W = wl["worlds"]
+    from madrona_b200 import sharding
+    first_world, _ = sharding.shard_range(W * world_size, world_size, rank)
     cfg = dict(wl["cfg"])
-    cfg["seed"] = int(cfg.get("seed", 0)) + rank * W       # disjoint worlds per rank
+    # world seeds depend on the GLOBAL world index: rank r simulates worlds [r*W, (r+1)*W)
+    cfg["seed"] = sharding.world_seed(int(cfg.get("seed", 0)), first_world, 0)
     ex = make_executor(wl["sim"], W, gpu_id=local_rank, **cfg)
     graph = ex.buildLaunchGraph(wl["taskgraphs"])
     launches_per_step = graph.num_kernels
@@ -219,7 +222,7 @@ def main():
     in_t = {s.name: ex.tensor(s.slot, s.dtype, (W,) + s.per_world) for s in desc.inputs}
     fixed_out = [s for s in desc.outputs if not s.dynamic and s.name in ("reward", "done")]
     out_t = {s.name: ex.tensor(s.slot, s.dtype, (W,) + s.per_world) for s in fixed_out}
-    gathered = {k: torch.empty((world_size,) + tuple(v.shape), dtype=v.dtype, device=dev)
+    gathered = {k: torch.empty((world_size * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
                 for k, v in out_t.items()} if world_size > 1 else {}
 
     n_act = 16
@@ -241,7 +244,7 @@ def main():
         ex.runAsync(graph, stream)
         if world_size > 1:
             for k, t in out_t.items():
-                dist.all_gather_into_tensor(gathered[k], t)
+                sharding.gather_exported(t, out=gathered[k])
         if host_io:
             for k, t in out_t.items():
                 pinned_out[k].copy_(t, non_blocking=True)

@@ -369,6 +369,10 @@ __device__ void rebuildWorldBVH(WorldBVH &bvh)
     }
 }
 
+__device__ void refitLeaf(WorldBVH &bvh, i32 leaf);
+
+// Rebuild (rare: after a reset) followed by the refit of every leaf of the
+// world, which the fused update+refit kernel skipped for this world.
 __device__ __forceinline__ void phaseRebuild(const EngineState &S, const PhysicsState &P, const i32 w, const int lane)
 {
     if (lane != 0) return;
@@ -376,6 +380,16 @@ __device__ __forceinline__ void phaseRebuild(const EngineState &S, const Physics
     if (!bvh.forceRebuild) return;
     bvh.forceRebuild = 0;
     rebuildWorldBVH(bvh);
+    for (u32 bi = 0; bi < P.numBodyArchetypes; bi++) {
+        const BodyArchetype &b = P.bodies[bi];
+        const TableDesc &t = S.tables[b.archetype];
+        const i32 first_row = t.worldOffsets[w];
+        const i32 num_rows = t.worldCounts[w];
+        for (i32 row = first_row; row < first_row + num_rows; row++) {
+            if (((const i32 *)t.columns[1])[row] != w) continue;
+            refitLeaf(bvh, bodyCol<i32>(S, b, PCLeafID, row));
+        }
+    }
 }
 
 // Grow-only refit: push the leaf's box into its slot, then keep growing
@@ -1890,7 +1904,13 @@ physBodyKernel(EngineState *Sp)
     for (i32 row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
         const i32 w = world_col[row];
         if (w < 0) continue;
-        if constexpr (OP == PhaseUpdateLeaves) rowUpdateLeaf(S, P, b, row, w);
+        if constexpr (OP == PhaseUpdateLeaves) {
+            // leaf update, then straight into the refit of that leaf (it only
+            // needs the leaf's own new box) -- unless the world asked for a
+            // rebuild, whose thread refits all leaves afterwards
+            rowUpdateLeaf(S, P, b, row, w);
+            if (!worldBVH(S, P, w).forceRebuild) rowRefit(S, P, b, row, w);
+        }
         else if constexpr (OP == PhaseRefit) rowRefit(S, P, b, row, w);
         else if constexpr (OP == PhaseIntegrate) rowIntegrate(S, P, b, row, w);
         else if constexpr (OP == PhaseSetVelocities) rowSetVelocity(S, P, b, row, w);
@@ -1906,9 +1926,31 @@ physRebuildKernel(EngineState *Sp)
     phaseRebuild(S, *S.physics, w, 0);
 }
 
+// lanes of a world's warp stride over its bodies (tables are world-sorted)
+template <typename Fn>
+__device__ __forceinline__ void forEachWorldBody(const EngineState &S, const PhysicsState &P, const i32 w,
+                                                 const int lane, Fn &&fn)
+{
+    for (u32 bi = 0; bi < P.numBodyArchetypes; bi++) {
+        const BodyArchetype &b = P.bodies[bi];
+        const TableDesc &t = S.tables[b.archetype];
+        const i32 first_row = t.worldOffsets[w];
+        const i32 num_rows = t.worldCounts[w];
+        for (i32 row = first_row + lane; row < first_row + num_rows; row += 32) {
+            if (((const i32 *)t.columns[1])[row] != w) continue;   // destroyed, awaiting compaction
+            fn(b, row);
+        }
+    }
+}
+
+// Neighbouring phases that share the warp-per-world mapping are fused into one
+// launch (flags): integrate -> narrowphase, and position solve -> velocity
+// update -> velocity solve.  Inside a world only __syncwarp is needed.
+constexpr u32 kFuseIntegrate = 1u, kFuseSetVelocities = 2u, kFuseSolveVelocities = 4u;
+
 template <u32 OP>
 __global__ void __launch_bounds__(32 * kPhysWarps, 8)
-physWorldKernel(EngineState *Sp)
+physWorldKernel(EngineState *Sp, u32 flags)
 {
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
@@ -1920,9 +1962,25 @@ physWorldKernel(EngineState *Sp)
         phaseFindCandidates(S, P, w, lane);
     } else if constexpr (OP == PhaseNarrowphase) {
         __shared__ LevelScratch scratch;
+        if (flags & kFuseIntegrate) {
+            forEachWorldBody(S, P, w, lane, [&](const BodyArchetype &b, i32 row) {
+                rowIntegrate(S, P, b, row, w);
+            });
+            __syncwarp();
+        }
         phaseNarrowphase(S, P, w, lane, warp, scratch);
     } else if constexpr (OP == PhaseSolvePositions) {
         phaseSolvePositions(S, P, w, lane);
+        if (flags & kFuseSetVelocities) {
+            __syncwarp();
+            forEachWorldBody(S, P, w, lane, [&](const BodyArchetype &b, i32 row) {
+                rowSetVelocity(S, P, b, row, w);
+            });
+        }
+        if (flags & kFuseSolveVelocities) {
+            __syncwarp();
+            phaseSolveVelocities(S, P, w, lane);
+        }
     } else if constexpr (OP == PhaseSolveVelocities) {
         phaseSolveVelocities(S, P, w, lane);
     }
@@ -2037,34 +2095,58 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
     const unsigned wgrid = (W + kPhysWarps - 1) / kPhysWarps;
     const unsigned wblock = 32 * kPhysWarps;
     const dim3 bgrid = bodyGrid(ex);
+    // which neighbouring phases share a launch (measured on B200: see DESIGN.md)
+    const u32 fuse = (u32)envU64p("MADRONA_B200_PHYS_FUSE", 0);
     for (uint32_t i = 0; i < count; i++) {
         const NodeRecord &rec = recs[i];
+        auto nextIs = [&](uint32_t ahead, u32 kind) {
+            return i + ahead < count && recs[i + ahead].kind == kind;
+        };
         switch (rec.kind) {
         case NodePhysBroadphaseUpdate:
+            // tag 0 (post-integration) never rebuilds in the reference either; a
+            // pending rebuild request then simply waits for the next tag-1 node,
+            // and the un-refitted leaves are refitted by that rebuild
             physBodyKernel<PhaseUpdateLeaves><<<bgrid, 256, 0, s>>>(d);
             if (rec.userTag == 1) physRebuildKernel<<<(W + 127) / 128, 128, 0, s>>>(d);
-            physBodyKernel<PhaseRefit><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysFindCandidates:
             // joints are iterated per world by the solver: keep their table in
             // world order (the reference sorts Joint here too, xpbd.cpp:1092-1096)
             launchSortArchetype(ex, ph->hPhys.jointArchetype, 1, s);
-            physWorldKernel<PhaseFindCandidates><<<wgrid, wblock, 0, s>>>(d);
+            physWorldKernel<PhaseFindCandidates><<<wgrid, wblock, 0, s>>>(d, 0u);
             break;
         case NodePhysSubstepBegin:
-            physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
+            if ((fuse & 1u) && nextIs(1, NodePhysNarrowphase)) {
+                physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d, kFuseIntegrate);
+                i += 1;
+            } else {
+                physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
+            }
             break;
         case NodePhysNarrowphase:
-            physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d);
+            physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d, 0u);
             break;
-        case NodePhysSolvePositions:
-            physWorldKernel<PhaseSolvePositions><<<wgrid, wblock, 0, s>>>(d);
+        case NodePhysSolvePositions: {
+            u32 flags = 0;
+            uint32_t skip = 0;
+            if ((fuse & 2u) && nextIs(1, NodePhysSetVelocities)) {
+                flags |= kFuseSetVelocities;
+                skip = 1;
+                if ((fuse & 4u) && nextIs(2, NodePhysSolveVelocities)) {
+                    flags |= kFuseSolveVelocities;
+                    skip = 2;
+                }
+            }
+            physWorldKernel<PhaseSolvePositions><<<wgrid, wblock, 0, s>>>(d, flags);
+            i += skip;
             break;
+        }
         case NodePhysSetVelocities:
             physBodyKernel<PhaseSetVelocities><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysSolveVelocities:
-            physWorldKernel<PhaseSolveVelocities><<<wgrid, wblock, 0, s>>>(d);
+            physWorldKernel<PhaseSolveVelocities><<<wgrid, wblock, 0, s>>>(d, 0u);
             break;
         default:
             *err = "unknown physics node kind " + std::to_string(rec.kind);

@@ -58,7 +58,21 @@ def run_reference(desc, num_worlds: int, num_steps: int, inputs: Optional[Dict[s
         out_path = os.path.join(tmp, "out.bin")
         if want_outputs:
             args += ["--out", out_path]
-        res = subprocess.run(args, capture_output=True, text=True, timeout=timeout)
+        # The reference's thread pool has a rare lost-wakeup race between
+        # ThreadPoolExecutor::run and workerThread (src/mw/cpu_exec.cpp:145-237:
+        # workerWakeup is reset by a worker after the main thread may already
+        # have re-armed it), which leaves the process asleep forever.  It is not
+        # ours to fix: run with a bounded timeout and retry.
+        attempts = 4
+        per_try = max(30.0, timeout / attempts)
+        res = None
+        for attempt in range(attempts):
+            try:
+                res = subprocess.run(args, capture_output=True, text=True, timeout=per_try)
+                break
+            except subprocess.TimeoutExpired:
+                if attempt == attempts - 1:
+                    raise
         if res.returncode != 0:
             raise RuntimeError(f"reference run failed: {res.stderr[-2000:]}")
         timing = json.loads(res.stdout.strip().splitlines()[-1])
