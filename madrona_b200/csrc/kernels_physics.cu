@@ -119,6 +119,7 @@ struct PJoint {         // == phys::JointConstraint (92 bytes)
 static_assert(sizeof(PJoint) == 92, "JointConstraint layout");
 
 constexpr u32 kRespDynamic = 0, kRespStatic = 2;
+constexpr int kPhysWarps = 2;     // worlds (warps) per block of the per-world physics kernels
 
 struct PhysicsHost {
     PhysicsState *dPhys = nullptr;
@@ -367,6 +368,25 @@ __device__ void rebuildWorldBVH(WorldBVH &bvh)
         parent.minX[slot] = merged.pMin.x; parent.minY[slot] = merged.pMin.y; parent.minZ[slot] = merged.pMin.z;
         parent.maxX[slot] = merged.pMax.x; parent.maxY[slot] = merged.pMax.y; parent.maxZ[slot] = merged.pMax.z;
     }
+
+    // report order of an un-pruned traversal (include/madrona/broadphase.inl:21-59)
+    i32 order_n = 0;
+    i32 walk[64];
+    walk[0] = 0;
+    i32 walk_n = 1;
+    while (walk_n > 0) {
+        const BVHNode &node = bvh.nodes[walk[--walk_n]];
+        for (int i = 0; i < 4; i++) {
+            const i32 child = node.children[i];
+            if (child == -1) continue;
+            if (child & 0x80000000) {
+                if (order_n < bvh.numAllocatedLeaves) bvh.traversalOrder[order_n++] = child & 0x7fffffff;
+            } else if (walk_n < 64) {
+                walk[walk_n++] = child;
+            }
+        }
+    }
+    bvh.numTraversal = order_n;
 }
 
 __device__ void refitLeaf(WorldBVH &bvh, i32 leaf);
@@ -490,12 +510,68 @@ __device__ __forceinline__ void forEachPartner(const WorldBVH &bvh, const PairVi
     }
 }
 
-__device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const i32 w, const int lane)
+constexpr int kMaxStagedLeaves = 64;
+
+struct StagedLeaf {
+    float box[6];       // the leaf's slot in its parent node (grow-only since the last rebuild)
+    i32 entityID;
+    u32 arch;
+    i32 row;
+    u32 prims;          // 0 => stale entity / not a rigid body: never a partner
+    u32 isStatic;
+};
+
+struct CandidateScratch {
+    StagedLeaf leaves[kPhysWarps][kMaxStagedLeaves];
+};
+
+// Candidate pairs of one world, in the CPU backend's order (bodies: archetype
+// ascending, then row; partners of a body: BVH report order).  The set a
+// traversal reports for body a is { leaf b : slotBox(b) overlaps leafBox(a) }
+// (ancestor boxes contain their leaves' slot boxes, so pruning removes nothing
+// else) and its order is the tree's fixed report order, so the search is a
+// uniform loop over the staged leaves instead of 32 divergent stack walks.
+__device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const i32 w, const int lane,
+                                    const int warp, CandidateScratch &scratch)
 {
     const WorldBVH &bvh = worldBVH(S, P, w);
     const PObjectManager &objs = *(const PObjectManager *)bvh.objMgr;
     Candidate *out = P.candidates + (size_t)w * P.maxCandidatesPerWorld;
+    StagedLeaf *staged = scratch.leaves[warp];
     i32 running = 0;
+
+    const i32 num_leaves = bvh.numTraversal;
+    if (num_leaves > kMaxStagedLeaves) {
+        // TODO(next round): window the staged list; sized for <= 64 bodies/world today
+        if (lane == 0) atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+        return;
+    }
+    // stage 1: lane k describes the k-th reported leaf
+    for (i32 k = lane; k < num_leaves; k += 32) {
+        const i32 leaf = bvh.traversalOrder[k];
+        const u32 packed_parent = bvh.leafParents[leaf];
+        const BVHNode &node = bvh.nodes[packed_parent >> 2];
+        const int slot = (int)(packed_parent & 3u);
+        StagedLeaf sl;
+        sl.box[0] = node.minX[slot]; sl.box[1] = node.minY[slot]; sl.box[2] = node.minZ[slot];
+        sl.box[3] = node.maxX[slot]; sl.box[4] = node.maxY[slot]; sl.box[5] = node.maxZ[slot];
+        const u64 packed = bvh.leafEntities[leaf];
+        sl.entityID = (i32)(u32)(packed >> 32);
+        const u32 gen = (u32)(packed & 0xFFFFFFFFull);
+        sl.arch = 0; sl.row = 0; sl.prims = 0; sl.isStatic = 0;
+        if (sl.entityID >= 0 && sl.entityID < S.entityCapacity) {
+            const EntitySlot es = S.entitySlots[sl.entityID];
+            const BodyArchetype *bb = es.gen == gen ? bodyOf(P, (u32)es.a) : nullptr;
+            if (bb) {
+                sl.arch = (u32)es.a;
+                sl.row = es.b;
+                sl.isStatic = bodyCol<u32>(S, *bb, PCResponseType, es.b) == kRespStatic ? 1u : 0u;
+                sl.prims = objs.primCounts[bodyCol<i32>(S, *bb, PCObjectID, es.b)];
+            }
+        }
+        staged[k] = sl;
+    }
+    __syncwarp();
 
     for (u32 bi = 0; bi < P.numBodyArchetypes; bi++) {
         const BodyArchetype &b = P.bodies[bi];
@@ -506,35 +582,31 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
             const i32 row = first + base + lane;
             const bool valid = base + lane < count && ((const i32 *)t.columns[1])[row] == w;
 
-            PairVisitor v { S, P, objs, 0, false, 0 };
+            i32 self_id = 0;
+            bool self_static = false;
+            u32 self_prims = 0;
             AABB box = AABB::invalid();
             if (valid) {
                 const u64 packed = ((const u64 *)t.columns[0])[row];
-                v.selfID = (i32)(u32)(packed >> 32);
-                v.selfStatic = bodyCol<u32>(S, b, PCResponseType, row) == kRespStatic;
-                v.selfPrims = objs.primCounts[bodyCol<i32>(S, b, PCObjectID, row)];
+                self_id = (i32)(u32)(packed >> 32);
+                self_static = bodyCol<u32>(S, b, PCResponseType, row) == kRespStatic;
+                self_prims = objs.primCounts[bodyCol<i32>(S, b, PCObjectID, row)];
                 const PAABB lb = bvh.leafAABBs[bodyCol<i32>(S, b, PCLeafID, row)];
                 box = AABB { { lb.pMin.x, lb.pMin.y, lb.pMin.z }, { lb.pMax.x, lb.pMax.y, lb.pMax.z } };
             }
 
-            // one traversal: remember the partners (in traversal order), count
-            // the candidates they stand for
-            constexpr int kKeep = 12;
-            u32 keep_arch[kKeep];
-            i32 keep_row[kKeep];
-            u32 keep_prims[kKeep];
-            int partners = 0;
+            // stage 2: which staged leaves does this body pair with (bit k)
+            unsigned long long partners = 0;
             i32 mine = 0;
-            if (valid) {
-                forEachPartner(bvh, v, box, [&](u32 b_arch, i32 b_row, u32 b_prims) {
-                    if (partners < kKeep) {
-                        keep_arch[partners] = b_arch;
-                        keep_row[partners] = b_row;
-                        keep_prims[partners] = b_prims;
-                    }
-                    partners++;
-                    mine += (i32)(v.selfPrims * b_prims);
-                });
+            for (i32 k = 0; k < num_leaves; k++) {
+                const StagedLeaf &sl = staged[k];
+                const AABB other { { sl.box[0], sl.box[1], sl.box[2] }, { sl.box[3], sl.box[4], sl.box[5] } };
+                const bool pair = valid && sl.prims != 0 && box.overlaps(other) &&
+                    self_id < sl.entityID && !(self_static && sl.isStatic);
+                if (pair) {
+                    partners |= 1ull << k;
+                    mine += (i32)(self_prims * sl.prims);
+                }
             }
             // exclusive scan across the warp = emission offsets in row order
             i32 incl = mine;
@@ -544,22 +616,16 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
             }
             const i32 total = __shfl_sync(0xffffffffu, incl, 31);
             i32 at = running + incl - mine;
-
-            auto emit = [&](u32 b_arch, i32 b_row, u32 b_prims) {
-                const u32 checks = v.selfPrims * b_prims;
+            while (partners) {
+                const int k = __ffsll((long long)partners) - 1;
+                partners &= partners - 1;
+                const StagedLeaf &sl = staged[k];
+                const u32 checks = self_prims * sl.prims;
                 for (u32 c = 0; c < checks; c++) {
                     if (at < P.maxCandidatesPerWorld) {
-                        out[at] = Candidate { b.archetype, row, b_arch, b_row,
-                                              c / b_prims, c % b_prims };
+                        out[at] = Candidate { b.archetype, row, sl.arch, sl.row, c / sl.prims, c % sl.prims };
                     }
                     at++;
-                }
-            };
-            if (valid && mine > 0) {
-                if (partners <= kKeep) {
-                    for (int k = 0; k < partners; k++) emit(keep_arch[k], keep_row[k], keep_prims[k]);
-                } else {
-                    forEachPartner(bvh, v, box, emit);   // rare: more partners than kept
                 }
             }
             running += total;
@@ -1390,7 +1456,6 @@ __device__ __forceinline__ i32 worldBodySlot(const EngineState &S, const Physics
 
 // one warp per world: candidates in order, contacts compacted in order, then
 // the dependency level of every contact (see Contact::level)
-constexpr int kPhysWarps = 2;     // worlds (warps) per block of the fused physics kernel
 
 struct LevelScratch {
     i32 lastLevel[kPhysWarps][kMaxLevelBodies];
@@ -1948,8 +2013,8 @@ __device__ __forceinline__ void forEachWorldBody(const EngineState &S, const Phy
 // update -> velocity solve.  Inside a world only __syncwarp is needed.
 constexpr u32 kFuseIntegrate = 1u, kFuseSetVelocities = 2u, kFuseSolveVelocities = 4u;
 
-template <u32 OP>
-__global__ void __launch_bounds__(32 * kPhysWarps, 8)
+template <u32 OP, int MINB>
+__global__ void __launch_bounds__(32 * kPhysWarps, MINB)
 physWorldKernel(EngineState *Sp, u32 flags)
 {
     EngineState &S = *Sp;
@@ -1959,7 +2024,8 @@ physWorldKernel(EngineState *Sp, u32 flags)
     const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (w >= (i32)S.numWorlds) return;
     if constexpr (OP == PhaseFindCandidates) {
-        phaseFindCandidates(S, P, w, lane);
+        __shared__ CandidateScratch cand_scratch;
+        phaseFindCandidates(S, P, w, lane, warp, cand_scratch);
     } else if constexpr (OP == PhaseNarrowphase) {
         __shared__ LevelScratch scratch;
         if (flags & kFuseIntegrate) {
@@ -2082,6 +2148,16 @@ static dim3 bodyGrid(Executor *ex)
     return dim3((unsigned)std::max(blocks, 1), std::max(P.numBodyArchetypes, 1u));
 }
 
+// min-blocks-per-SM variant of the per-world kernels (register budget =
+// 65536 / (64 * MINB)): 8 -> 128 regs, 12 -> 85, 16 -> 64
+template <u32 OP>
+static void launchWorld(int minb, unsigned grid, unsigned block, cudaStream_t s, EngineState *d, u32 flags)
+{
+    if (minb >= 16) physWorldKernel<OP, 16><<<grid, block, 0, s>>>(d, flags);
+    else if (minb >= 12) physWorldKernel<OP, 12><<<grid, block, 0, s>>>(d, flags);
+    else physWorldKernel<OP, 8><<<grid, block, 0, s>>>(d, flags);
+}
+
 bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, cudaStream_t s,
                          std::string *err)
 {
@@ -2097,6 +2173,10 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
     const dim3 bgrid = bodyGrid(ex);
     // which neighbouring phases share a launch (measured on B200: see DESIGN.md)
     const u32 fuse = (u32)envU64p("MADRONA_B200_PHYS_FUSE", 0);
+    const int mb_cand = (int)envU64p("MADRONA_B200_MINB_CAND", 8);
+    const int mb_narrow = (int)envU64p("MADRONA_B200_MINB_NARROW", 8);
+    const int mb_pos = (int)envU64p("MADRONA_B200_MINB_POS", 8);
+    const int mb_vel = (int)envU64p("MADRONA_B200_MINB_VEL", 8);
     for (uint32_t i = 0; i < count; i++) {
         const NodeRecord &rec = recs[i];
         auto nextIs = [&](uint32_t ahead, u32 kind) {
@@ -2114,18 +2194,18 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
             // joints are iterated per world by the solver: keep their table in
             // world order (the reference sorts Joint here too, xpbd.cpp:1092-1096)
             launchSortArchetype(ex, ph->hPhys.jointArchetype, 1, s);
-            physWorldKernel<PhaseFindCandidates><<<wgrid, wblock, 0, s>>>(d, 0u);
+            launchWorld<PhaseFindCandidates>(mb_cand, wgrid, wblock, s, d, 0u);
             break;
         case NodePhysSubstepBegin:
             if ((fuse & 1u) && nextIs(1, NodePhysNarrowphase)) {
-                physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d, kFuseIntegrate);
+                launchWorld<PhaseNarrowphase>(mb_narrow, wgrid, wblock, s, d, kFuseIntegrate);
                 i += 1;
             } else {
                 physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
             }
             break;
         case NodePhysNarrowphase:
-            physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d, 0u);
+            launchWorld<PhaseNarrowphase>(mb_narrow, wgrid, wblock, s, d, 0u);
             break;
         case NodePhysSolvePositions: {
             u32 flags = 0;
@@ -2138,7 +2218,7 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
                     skip = 2;
                 }
             }
-            physWorldKernel<PhaseSolvePositions><<<wgrid, wblock, 0, s>>>(d, flags);
+            launchWorld<PhaseSolvePositions>(mb_pos, wgrid, wblock, s, d, flags);
             i += skip;
             break;
         }
@@ -2146,7 +2226,7 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
             physBodyKernel<PhaseSetVelocities><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysSolveVelocities:
-            physWorldKernel<PhaseSolveVelocities><<<wgrid, wblock, 0, s>>>(d, 0u);
+            launchWorld<PhaseSolveVelocities>(mb_vel, wgrid, wblock, s, d, 0u);
             break;
         default:
             *err = "unknown physics node kind " + std::to_string(rec.kind);

@@ -47,6 +47,11 @@ struct WorldBVH {
     LeafTransform *leafTransforms;
     u32 *leafParents;         // (node << 2) | child
     i32 *sortedLeaves;
+    // Leaves in the order an un-pruned traversal reports them (children 0..3
+    // scanned in order, inner children visited LIFO).  Pruning never reorders
+    // the survivors, so a query's result list is this list filtered by box
+    // overlap -- which lets the candidate search run as a uniform loop.
+    i32 *traversalOrder;
     i32 numNodes;
     i32 numAllocatedNodes;
     i32 numLeaves;
@@ -54,7 +59,7 @@ struct WorldBVH {
     float velExpansion;
     float accelExpansion;
     i32 forceRebuild;
-    i32 pad;
+    i32 numTraversal;
 };
 
 // == phys::PhysicsSystemState (src/physics/physics_impl.hpp:7-15)

@@ -313,6 +313,8 @@ inline void init(Context &ctx,
     bvh.leafTransforms = (mb2::LeafTransform *)carve(sizeof(mb2::LeafTransform) * max_leaves);
     bvh.leafParents = (uint32_t *)carve(4 * max_leaves);
     bvh.sortedLeaves = (int32_t *)carve(4 * max_leaves);
+    bvh.traversalOrder = (int32_t *)carve(4 * max_leaves);
+    bvh.numTraversal = 0;
     bvh.numNodes = 0;
     bvh.numAllocatedNodes = (int32_t)num_nodes;
     bvh.numLeaves = 0;
