@@ -40,7 +40,7 @@ int main(int argc, char **argv)
         fprintf(stderr, "--objects <blob> required\n");
         return 1;
     }
-    Config cfg { loadObjects(objects_path), (uint32_t)(args.extra[0] ? args.extra[0] : 100), 0 };
+    Config cfg { loadObjects(objects_path), (uint32_t)(args.extra[0] ? args.extra[0] : 100), (uint32_t)args.extra[2] };
     std::vector<WorldInit> inits(args.numWorlds);
     for (int64_t i = 0; i < args.numWorlds; i++) inits[i].seed = (uint32_t)(args.extra[1] + i);
 

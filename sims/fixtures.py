@@ -55,7 +55,8 @@ def _grid_init(w, cfg):
 
 
 def _room_cfg(cfg):
-    return struct.pack("<QII", int(cfg.get("obj_mgr_ptr", 0)), int(cfg["episode_len"]), 0)
+    return struct.pack("<QII", int(cfg.get("obj_mgr_ptr", 0)), int(cfg["episode_len"]),
+                       int(cfg.get("grab_period", 0)))
 
 
 def _room_init(w, cfg):
@@ -68,6 +69,21 @@ def _room_objects():
 
 
 SIMS: Dict[str, SimDesc] = {
+    # GPU-only: custom-key SortArchetypeNode, checked against oracle/restate.py
+    "sortcheck": SimDesc(
+        name="sortcheck",
+        sources=[os.path.join(_ROOT, "sortcheck", "sim.cpp")],
+        num_exports=4,
+        num_taskgraphs=1,
+        inputs=[],
+        outputs=[Slot(0, "key", "uint32", (1,), dynamic=True),
+                 Slot(1, "payload", "uint32", (4,), dynamic=True),
+                 Slot(2, "tag", "uint8", (6,), dynamic=True)],
+        pack_config=lambda cfg: struct.pack("<II", int(cfg["items_per_world"]), int(cfg["key_mask"])),
+        pack_init=lambda w, cfg: struct.pack("<I", int(cfg.get("seed", 0)) + w),
+        oracle_extra=lambda cfg: [],
+        defaults={"items_per_world": 9, "key_mask": 0xFFFFFFFF, "seed": 0},
+    ),
     "room": SimDesc(
         name="room",
         sources=[os.path.join(_ROOT, "room", "sim.cpp")],
@@ -84,8 +100,9 @@ SIMS: Dict[str, SimDesc] = {
                  Slot(12, "body_vel", "float32", (6,), dynamic=True)],
         pack_config=_room_cfg,
         pack_init=_room_init,
-        oracle_extra=lambda cfg: [int(cfg["episode_len"]), int(cfg.get("seed", 0))],
-        defaults={"episode_len": 100, "seed": 0},
+        oracle_extra=lambda cfg: [int(cfg["episode_len"]), int(cfg.get("seed", 0)),
+                                  int(cfg.get("grab_period", 0))],
+        defaults={"episode_len": 100, "seed": 0, "grab_period": 0},
         objects=_room_objects,
     ),
     "gridworld": SimDesc(

@@ -206,6 +206,10 @@ inline void resetSystem(Engine &ctx, WorldReset &reset)
     }
     if (should_reset) {
         reset.reset = 0;
+        if (sim.hasJoint != 0) {
+            ctx.destroyEntity(sim.joint);
+            sim.hasJoint = 0;
+        }
         for (int32_t i = 0; i < kNumCubes; i++) {
             ctx.destroyEntity(sim.cubes[i]);
         }
@@ -213,6 +217,38 @@ inline void resetSystem(Engine &ctx, WorldReset &reset)
     }
     ctx.singleton<BodyCount>().count =
         1 + kNumBorderWalls + kNumInnerWalls + kNumPillars + kNumCubes;
+}
+
+// One invocation per world.  Toggle a fixed joint between agent 0 and a cube.
+inline void grabSystem(Engine &ctx, BodyCount &)
+{
+    Sim &sim = ctx.data();
+    if (sim.grabPeriod == 0) {
+        return;
+    }
+    sim.stepCount += 1;
+    if (sim.stepCount % sim.grabPeriod != 0) {
+        return;
+    }
+    if (sim.hasJoint != 0) {
+        ctx.destroyEntity(sim.joint);
+        sim.hasJoint = 0;
+        return;
+    }
+    Entity agent = sim.agents[0];
+    Vector3 agent_pos = ctx.get<Position>(agent);
+    Quat agent_rot = ctx.get<Rotation>(agent);
+    Vector3 hold_point = agent_pos + agent_rot.rotateVec(Vector3 { 0.f, 1.75f, 0.f });
+    for (int32_t i = 0; i < kNumCubes; i++) {
+        Vector3 cube_pos = ctx.get<Position>(sim.cubes[i]);
+        if (cube_pos.distance2(hold_point) < 4.f) {
+            sim.joint = PhysicsSystem::makeFixedJoint(ctx, agent, sim.cubes[i],
+                Quat { 1, 0, 0, 0 }, Quat { 1, 0, 0, 0 },
+                Vector3 { 0.f, 1.75f, 0.f }, Vector3 { 0.f, 0.f, 0.f }, 0.f);
+            sim.hasJoint = 1;
+            break;
+        }
+    }
 }
 
 inline void observationSystem(Engine &, Position &pos, Rotation &rot,
@@ -285,8 +321,10 @@ void Sim::setupTasks(TaskGraphManager &mgr, const Config &)
         Velocity, Action>>({physics});
     auto cleanup = PhysicsSystem::setupCleanupTasks(builder, {zero_vel});
 
+    auto grab = builder.addToGraph<ParallelForNode<Engine, grabSystem,
+        BodyCount>>({cleanup});
     auto reward = builder.addToGraph<ParallelForNode<Engine, rewardSystem,
-        Position, Progress, Reward, StepsRemaining, Done>>({cleanup});
+        Position, Progress, Reward, StepsRemaining, Done>>({grab});
     auto reset = builder.addToGraph<ParallelForNode<Engine, resetSystem,
         WorldReset>>({reward});
 
@@ -316,7 +354,11 @@ Sim::Sim(Engine &ctx, const Config &cfg, const WorldInit &init)
     : WorldBase(ctx),
       rng(init.seed),
       episodeLen(cfg.episodeLen),
-      episode(0)
+      episode(0),
+      grabPeriod(cfg.grabPeriod),
+      stepCount(0),
+      hasJoint(0),
+      joint(Entity::none())
 {
     PhysicsSystem::init(ctx, cfg.objMgr, kDeltaT, kNumSubsteps,
                         -9.8f * math::up, kMaxBodies);

@@ -119,7 +119,9 @@ struct PhysicsEntity : public madrona::Archetype<
 struct Config {
     madrona::phys::ObjectManager *objMgr;
     uint32_t episodeLen;
-    uint32_t pad;
+    // > 0: every grabPeriod steps agent 0 grabs the next cube in reach with a
+    // fixed joint, or lets go of the one it holds (exercises JointConstraint)
+    uint32_t grabPeriod;
 };
 
 struct WorldInit {
@@ -144,6 +146,11 @@ struct Sim : public madrona::WorldBase {
     Entity pillars[kNumPillars];
     Entity cubes[kNumCubes];
     Entity agents[kNumAgents];
+
+    uint32_t grabPeriod;
+    uint32_t stepCount;
+    uint32_t hasJoint;
+    Entity joint;
 };
 
 class Engine : public madrona::CustomContext<Engine, Sim> {

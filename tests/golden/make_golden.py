@@ -28,6 +28,8 @@ CASES = [
      {"grid_size": 3, "episode_len": 97, "init_items": 20, "seed": 3}),
     # rigid-body room: two resets inside the trace (episode_len 100 + random resets)
     ("room_w4_s210", "room", 4, 210, {"episode_len": 100, "seed": 21}),
+    # same fixture with agent 0 grabbing / releasing cubes through fixed joints
+    ("room_grab_w3_s120", "room", 3, 120, {"episode_len": 70, "seed": 5, "grab_period": 5}),
 ]
 
 if __name__ == "__main__":

@@ -63,3 +63,35 @@ def test_gpu_matches_live_reference_many_worlds():
     ref, _ = runner.run_reference(SIMS["room"], W, steps, ins, cfg, workers=4)
     got, _ = rollout_gpu("room", W, steps, ins, cfg)
     assert_traces_equal(got, ref, exact=EXACT, rtol=1e-4, atol=1e-5)
+
+
+GRAB_CFG = {"episode_len": 70, "seed": 5, "grab_period": 5}
+
+
+def test_grab_golden_has_joint_effects():
+    W, steps, ins, outs = load_golden("room_grab_w3_s120")
+    base, _ = (runner.run_reference(SIMS["room"], W, steps, ins, {"episode_len": 70, "seed": 5}, workers=1)
+               if runner.available("room") else (None, None))
+    if base is not None:
+        diff = max(float(np.abs(a - b).max()) for a, b in zip(outs["body_pos"], base["body_pos"]))
+        assert diff > 0.1          # joints really moved cubes
+
+
+@pytest.mark.gpu
+def test_gpu_joints_match_golden():
+    # fixed joints (makeFixedJoint / destroyEntity on the Joint archetype, solved
+    # after the contacts each substep: xpbd.cpp:607-736)
+    W, steps, ins, outs = load_golden("room_grab_w3_s120")
+    got, _ = rollout_gpu("room", W, steps, ins, GRAB_CFG)
+    assert_traces_equal(got, outs, exact=EXACT, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not runner.available("room"), reason="oracle/_ref not built")
+def test_gpu_joints_match_live_reference():
+    W, steps = 200, 90
+    cfg = {"episode_len": 50, "seed": 77, "grab_period": 3}
+    ins = make_inputs("room", W, steps, seed=4)
+    ref, _ = runner.run_reference(SIMS["room"], W, steps, ins, cfg, workers=4)
+    got, _ = rollout_gpu("room", W, steps, ins, cfg)
+    assert_traces_equal(got, ref, exact=EXACT, rtol=1e-4, atol=1e-5)
