@@ -141,6 +141,8 @@ def run_reference_arm(args, wl):
     except Exception:
         pass
     W = wl["ref_worlds"]
+    if not W:
+        return None   # GPU-only microbenchmark: no CPU-backend counterpart
     steps = getattr(args, "ref_steps", None) or (args.steps + args.warmup)
     if not runner.available(desc.name):
         return None

@@ -593,6 +593,16 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
                    cudaMemcpyDeviceToHost);
         cudaEventRecord(ev[0], ex->stream);
         for (size_t k = 0; k < order.size(); k++) {
+            const NodeRecord &nr = S.nodes[order[k]];
+            if (nr.kind == NodeSortArchetype || nr.kind == NodeCompactArchetype) {
+                // whether this sort will actually run (and over how many rows) is only
+                // known once the preceding nodes have executed: look now (the extra
+                // sync sits between two event pairs, it is not timed)
+                cudaStreamSynchronize(ex->stream);
+                cudaMemcpy(&tables[nr.archetype], &ex->dState->tables[nr.archetype], sizeof(TableDesc),
+                           cudaMemcpyDeviceToHost);
+                cudaEventRecord(ev[k], ex->stream);
+            }
             if (!enqueueNode(ex, order[k], ex->stream)) return -1;
             cudaEventRecord(ev[k + 1], ex->stream);
         }

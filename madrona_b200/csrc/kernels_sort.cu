@@ -258,22 +258,34 @@ sortOnesweepKernel(SortParams p, int pass)
 }
 
 // ---- kernel P+2: fused multi-column permutation ------------------------------------
+// A block owns tiles of kRearrangeTile consecutive OUTPUT rows: the tile's slice
+// of the permutation is staged in shared memory once and reused for every
+// column, each column is moved in its widest aligned unit (16/8/4/1 bytes) with
+// coalesced stores (source rows are mostly in order, so the gathers coalesce
+// too).  The same pass re-points entity slots, derives worldOffsets/worldCounts
+// from the sorted keys and wipes the look-back scratch; the last block flips
+// the column pointers and publishes the new row count.
+constexpr int kRearrangeTile = 2048;
+
 template <typename UnitT>
-__device__ __forceinline__ void gatherUnits(const void *src_v, void *dst_v,
-                                            const int32_t *perm, int32_t new_n,
-                                            uint32_t units_per_row,
-                                            int64_t first, int64_t stride)
+__device__ __forceinline__ void gatherTile(const void *src_v, void *dst_v, const int32_t *perm_s,
+                                           int32_t tile_row0, int32_t rows, uint32_t units_per_row)
 {
     const UnitT *src = (const UnitT *)src_v;
-    UnitT *dst = (UnitT *)dst_v;
-    const int64_t total = (int64_t)new_n * units_per_row;
+    UnitT *dst = (UnitT *)dst_v + (size_t)tile_row0 * units_per_row;
+    const uint32_t total = (uint32_t)rows * units_per_row;
     if (units_per_row == 1) {
-        for (int64_t u = first; u < total; u += stride) dst[u] = src[perm[u]];
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = src[perm_s[i]];
+    } else if ((units_per_row & (units_per_row - 1)) == 0) {
+        const int sh = __ffs(units_per_row) - 1;
+        const uint32_t mask = units_per_row - 1;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            dst[i] = src[((size_t)perm_s[i >> sh] << sh) + (i & mask)];
+        }
     } else {
-        for (int64_t u = first; u < total; u += stride) {
-            const int32_t row = (int32_t)(u / units_per_row);
-            const uint32_t k = (uint32_t)(u - (int64_t)row * units_per_row);
-            dst[u] = src[(int64_t)perm[row] * units_per_row + k];
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint32_t r = i / units_per_row;
+            dst[i] = src[(size_t)perm_s[r] * units_per_row + (i - r * units_per_row)];
         }
     }
 }
@@ -288,63 +300,82 @@ sortRearrangeKernel(SortParams p)
     const int last = (p.numPasses - 1) & 1;
     const int32_t *perm = p.idx[last];
     const uint32_t *sorted_keys = p.keys[last];
-    const int32_t col = blockIdx.y;
 
-    if (col < t.numColumns) {
-        const void *src = t.columns[col];
-        void *dst = p.alt[col];
-        const uint32_t bytes = t.columnBytes[col];
-        const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    __shared__ int32_t perm_s[kRearrangeTile];
 
-        if (col == 0) {
-            // Entity column: move + re-point the entity slot at the new row
-            // (sort_archetype.cpp:1357-1379)
-            const unsigned long long *s = (const unsigned long long *)src;
-            unsigned long long *d = (unsigned long long *)dst;
-            EntitySlot *slots = p.state->entitySlots;
-            for (int64_t r = first; r < new_n; r += stride) {
-                unsigned long long e = s[perm[r]];
-                d[r] = e;
-                const uint32_t gen = (uint32_t)(e & 0xFFFFFFFFull);
-                const int32_t id = (int32_t)(uint32_t)(e >> 32);
-                if (id >= 0 && gen != 0xFFFFFFFFu && id < p.state->entityCapacity &&
-                        slots[id].gen == gen && slots[id].a == (int32_t)p.archetype) {
-                    slots[id].b = (int32_t)r;
+    // scratch of the finished radix passes: wiped here, spread over all blocks
+    {
+        const int64_t tiles = (n + kTileItems - 1) / kTileItems;
+        const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+        for (int pass = 0; pass < p.numPasses; pass++) {
+            uint32_t *lb = p.lookback + (size_t)pass * p.maxTiles * 256;
+            for (int64_t i = gtid; i < tiles * 256; i += gstride) lb[i] = 0;
+        }
+        for (int64_t i = gtid; i < p.numPasses * 256; i += gstride) p.bins[i] = 0;
+    }
+
+    const int32_t num_tiles = (new_n + kRearrangeTile - 1) / kRearrangeTile;
+    for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int32_t row0 = tile * kRearrangeTile;
+        const int32_t rows = min(kRearrangeTile, new_n - row0);
+        __syncthreads();
+        for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
+        __syncthreads();
+
+        for (int32_t col = 0; col < t.numColumns; col++) {
+            const void *src = t.columns[col];
+            void *dst = p.alt[col];
+            const uint32_t bytes = t.columnBytes[col];
+            if (col == 0) {
+                // Entity column: move + re-point the entity slot at the new row
+                // (sort_archetype.cpp:1357-1379)
+                const unsigned long long *sp = (const unsigned long long *)src;
+                unsigned long long *dp = (unsigned long long *)dst;
+                EntitySlot *slots = p.state->entitySlots;
+                for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) {
+                    const unsigned long long e = sp[perm_s[i]];
+                    dp[row0 + i] = e;
+                    const uint32_t gen = (uint32_t)(e & 0xFFFFFFFFull);
+                    const int32_t id = (int32_t)(uint32_t)(e >> 32);
+                    if (id >= 0 && gen != 0xFFFFFFFFu && id < p.state->entityCapacity &&
+                            slots[id].gen == gen && slots[id].a == (int32_t)p.archetype) {
+                        slots[id].b = row0 + i;
+                    }
                 }
+            } else if ((bytes & 15u) == 0) {
+                gatherTile<uint4>(src, dst, perm_s, row0, rows, bytes >> 4);
+            } else if ((bytes & 7u) == 0) {
+                gatherTile<uint2>(src, dst, perm_s, row0, rows, bytes >> 3);
+            } else if ((bytes & 3u) == 0) {
+                gatherTile<uint32_t>(src, dst, perm_s, row0, rows, bytes >> 2);
+            } else {
+                gatherTile<unsigned char>(src, dst, perm_s, row0, rows, bytes);
             }
-        } else if ((bytes & 15u) == 0) {
-            gatherUnits<uint4>(src, dst, perm, new_n, bytes >> 4, first, stride);
-        } else if ((bytes & 7u) == 0) {
-            gatherUnits<uint2>(src, dst, perm, new_n, bytes >> 3, first, stride);
-        } else if ((bytes & 3u) == 0) {
-            gatherUnits<uint32_t>(src, dst, perm, new_n, bytes >> 2, first, stride);
-        } else {
-            gatherUnits<unsigned char>(src, dst, perm, new_n, bytes, first, stride);
         }
 
-        // world boundaries from the sorted keys (done by the WorldID column's blocks)
-        if (col == 1 && p.worldSort) {
-            for (int64_t r = first; r < new_n; r += stride) {
+        // world boundaries from the sorted keys
+        if (p.worldSort) {
+            for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) {
+                const int32_t r = row0 + i;
                 const uint32_t k = sorted_keys[r];
                 if (r == 0 || sorted_keys[r - 1] != k) {
-                    int32_t end = (int32_t)r + 1;
+                    int32_t end = r + 1;
                     while (end < new_n && sorted_keys[end] == k) end++;
-                    t.worldOffsets[k] = (int32_t)r;
-                    t.worldCounts[k] = end - (int32_t)r;
+                    t.worldOffsets[k] = r;
+                    t.worldCounts[k] = end - r;
                 }
             }
         }
     }
 
-    // ---- last block out: flip column buffers, publish the new row count,
-    // reset the scratch for the next sort.
+    // ---- last block out: flip column buffers, publish the new row count
     __shared__ bool is_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         int32_t done = atomicAdd(&p.ctrl->blocksDone, 1);
-        is_last = done == (int32_t)(gridDim.x * gridDim.y) - 1;
+        is_last = done == (int32_t)gridDim.x - 1;
     }
     __syncthreads();
     if (!is_last) return;
@@ -354,12 +385,6 @@ sortRearrangeKernel(SortParams p)
         void *old_main = t.columns[c];
         t.columns[c] = p.alt[c];
         p.alt[c] = old_main;
-    }
-    for (int i = threadIdx.x; i < p.numPasses * 256; i += blockDim.x) p.bins[i] = 0;
-    const int32_t tiles = (n + kTileItems - 1) / kTileItems;
-    for (int pass = 0; pass < p.numPasses; pass++) {
-        uint32_t *lb = p.lookback + (size_t)pass * p.maxTiles * 256;
-        for (int64_t i = threadIdx.x; i < (int64_t)tiles * 256; i += blockDim.x) lb[i] = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -538,9 +563,11 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
     for (int pass = 0; pass < p.numPasses; pass++) {
         sortOnesweepKernel<<<sweep_grid, kSortThreads, 0, s>>>(p, pass);
     }
+    const int rtiles = (t.capacity + kRearrangeTile - 1) / kRearrangeTile;
+    const int rblocks = std::max(1, std::min(rtiles, ex->numSMs * 4));
+    sortRearrangeKernel<<<rblocks, 256, 0, s>>>(p);
     const int row_blocks = std::max(1, std::min((t.capacity + 255) / 256, ex->numSMs * 2));
     dim3 rgrid((unsigned)row_blocks, (unsigned)t.numColumns);
-    sortRearrangeKernel<<<rgrid, 256, 0, s>>>(p);
 
     if (mask) sortCopyBackKernel<<<rgrid, 256, 0, s>>>(p, mask);
 }
