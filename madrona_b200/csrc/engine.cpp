@@ -582,8 +582,9 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
         }
     }
     std::vector<NodeProfile> prof(order.size());
-    std::vector<cudaEvent_t> ev(order.size() + 1);
+    std::vector<cudaEvent_t> ev(order.size() + 1), ev_start(order.size());
     for (auto &e : ev) cudaEventCreate(&e);
+    for (auto &e : ev_start) cudaEventCreate(&e);
     std::vector<TableDesc> tables(S.numArchetypes);
 
     for (uint32_t rep = 0; rep < reps + 1; rep++) {   // rep 0 = warm-up
@@ -601,8 +602,8 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
                 cudaStreamSynchronize(ex->stream);
                 cudaMemcpy(&tables[nr.archetype], &ex->dState->tables[nr.archetype], sizeof(TableDesc),
                            cudaMemcpyDeviceToHost);
-                cudaEventRecord(ev[k], ex->stream);
             }
+            cudaEventRecord(ev_start[k], ex->stream);
             if (!enqueueNode(ex, order[k], ex->stream)) return -1;
             cudaEventRecord(ev[k + 1], ex->stream);
         }
@@ -613,7 +614,7 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
         if (rep == 0) continue;
         for (size_t k = 0; k < order.size(); k++) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+            cudaEventElapsedTime(&ms, ev_start[k], ev[k + 1]);
             const NodeRecord &r = S.nodes[order[k]];
             NodeProfile &p = prof[k];
             p.ms += ms;
@@ -649,6 +650,7 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
         }
     }
     for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e : ev_start) cudaEventDestroy(e);
 
     static const char *kind_names[] = { "parallel_for", "sort_archetype", "compact_archetype",
                                         "clear_tmp", "reset_tmp_alloc", "recycle_entities" };
