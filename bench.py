@@ -220,6 +220,9 @@ def main():
     ex = make_executor(wl["sim"], W, gpu_id=local_rank, **cfg)
     graph = ex.buildLaunchGraph(wl["taskgraphs"])
     launches_per_step = graph.num_kernels
+    render_graph = ex.buildRenderGraph() if wl.get("render") else None
+    if render_graph is not None:
+        launches_per_step += render_graph.num_kernels
 
     in_t = {s.name: ex.tensor(s.slot, s.dtype, (W,) + s.per_world) for s in desc.inputs}
     fixed_out = [s for s in desc.outputs if not s.dynamic and s.name in ("reward", "done")]
@@ -244,6 +247,8 @@ def main():
             for k, t in in_t.items():
                 t.copy_(dev_actions[k][i % n_act], non_blocking=True)
         ex.runAsync(graph, stream)
+        if render_graph is not None:
+            ex.runAsync(render_graph, stream)
         if world_size > 1:
             for k, t in out_t.items():
                 sharding.gather_exported(t, out=gathered[k])
@@ -292,6 +297,21 @@ def main():
         peak, peak_kind = load_peaks()
         prof = ex.profileNodes(wl["taskgraphs"], reps=20)
         prof = [p for p in prof if p["bytes"] > 0 and p["ms"] > 0]
+        if render_graph is not None:
+            # the ray caster is its own launch graph: time it with events on the same stream
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            reps = 10
+            ex.runAsync(render_graph, stream)
+            evs[0].record(stream)
+            for _ in range(reps):
+                ex.runAsync(render_graph, stream)
+            evs[1].record(stream)
+            torch.cuda.synchronize()
+            res = int(cfg.get("resolution", 64))
+            views = ex.exportedNumRows(14)
+            per_px = 8 if cfg.get("rgbd") else 4
+            prof.append({"kind": "raycast", "node": -1, "ms": evs[0].elapsed_time(evs[1]) / reps,
+                         "rows": float(views), "bytes": float(views * res * res * per_px)})
         if prof:
             # dominant kernel = the node kind with the largest share of the step
             kinds = {}

@@ -15,4 +15,11 @@ EXTRA_WORKLOADS["sortcheck"] = dict(
     ref_worlds=0, taskgraphs=[0],
     desc="ECS-sort microbenchmark: 65536 worlds x 48 rows (3.1M rows, 38 B/row), every step re-keys all rows "
          "and runs SortArchetypeNode<Item, SortKey> (4 radix passes + fused 5-column permutation)")
+# BASELINE.json configs[3]: "Escape Room 16384 worlds/GPU with 64x64 batch ray-traced observations"
+EXTRA_WORKLOADS["room_render"] = dict(
+    sim="room_render", worlds=16384,
+    cfg={"episode_len": 200, "seed": 0, "resolution": 64, "rgbd": True},
+    ref_worlds=0, taskgraphs=[0], render=True,
+    desc="rigid-body room + 2 cameras/world, 64x64 RGBA8 + f32 depth by the batch ray caster "
+         "(BASELINE configs[3] class; GPU only: the reference CPU backend cannot ray cast)")
 EXTRA_DEFAULT = "room"

@@ -314,7 +314,7 @@ static bool createExecutor(Executor *ex, const mb2_state_config *sc,
 
     // engine-owned systems get their device blocks before registerTypes so the
     // simulator's calls into PhysicsSystem / RenderingSystem can record into them
-    if (!physicsHostCreate(ex, &err)) {
+    if (!physicsHostCreate(ex, &err) || !renderHostCreate(ex, rc, &err)) {
         setError(err);
         return false;
     }
@@ -349,7 +349,7 @@ static bool createExecutor(Executor *ex, const mb2_state_config *sc,
         setError(err);
         return false;
     }
-    if (!physicsHostAfterRegistry(ex, rc, &err)) {
+    if (!physicsHostAfterRegistry(ex, rc, &err) || !renderHostAfterRegistry(ex, &err)) {
         setError(err);
         return false;
     }
@@ -423,6 +423,7 @@ static void destroyExecutor(Executor *ex)
     cudaSetDevice(ex->gpu);
     if (ex->stream) cudaStreamSynchronize(ex->stream);
     physicsHostDestroy(ex);
+    renderHostDestroy(ex);
     sortScratchDestroy(ex);
     for (void *p : ex->allocations) cudaFree(p);
     if (ex->hStatus) cudaFreeHost(ex->hStatus);
@@ -475,6 +476,14 @@ static bool enqueueNode(Executor *ex, uint32_t node_idx, cudaStream_t s)
         // IDs are recycled at destroy time through the per-world caches
         // (state.hpp releaseEntityLocked); nothing left to do here.
         return true;
+    case NodeRenderPrepare: {
+        std::string err;
+        if (!renderEnqueuePrepare(ex, s, &err)) {
+            setError(err);
+            return false;
+        }
+        return true;
+    }
     default:
         if (r.kind >= NodePhysBroadphaseUpdate) {
             std::string err;

@@ -272,6 +272,7 @@ bool jitCompile(const std::vector<std::string> &sources,
         std::string body;
         if (readFile(csrc_inc + "/mb2_state.h", &body)) h = hashString(h, body);
         if (readFile(csrc_inc + "/physics_state.h", &body)) h = hashString(h, body);
+        if (readFile(csrc_inc + "/render_state.h", &body)) h = hashString(h, body);
     }
     for (const std::string &f : user_flags) {
         if (f.rfind("-I", 0) == 0) hashDir(&h, f.substr(2));

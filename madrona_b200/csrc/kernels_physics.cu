@@ -2282,10 +2282,4 @@ uint64_t physicsNodeBytes(Executor *ex, const NodeRecord &rec, const char **name
     }
 }
 
-LaunchGraph *physicsBuildRenderGraph(Executor *, std::string *err)
-{
-    *err = "batch ray-cast renderer is not part of this build (SURVEY.md 8 rows a13-a15: next round)";
-    return nullptr;
-}
-
 }

@@ -13,6 +13,11 @@ bool physicsEnqueueNode(Executor *ex, const NodeRecord &rec, cudaStream_t s, std
 bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, cudaStream_t s,
                          std::string *err);
 LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err);
+// batch ray-cast renderer (kernels_render.cu)
+bool renderHostCreate(Executor *ex, const mb2_render_config *rc, std::string *err);
+bool renderHostAfterRegistry(Executor *ex, std::string *err);
+void renderHostDestroy(Executor *ex);
+bool renderEnqueuePrepare(Executor *ex, cudaStream_t s, std::string *err);
 // algorithmic bytes of one launch of a physics node + a short name (profiling)
 uint64_t physicsNodeBytes(Executor *ex, const NodeRecord &rec, const char **name, int64_t *rows);
 

@@ -36,6 +36,10 @@ class SimDesc:
     defaults: Dict = field(default_factory=dict)
     # () -> (blob, relocs): ObjectManager blob whose address goes into Config
     objects: Callable = None
+    # extra NVRTC flags (e.g. a build variant of the same sources)
+    compile_flags: List[str] = field(default_factory=list)
+    # batch ray-cast renderer: (cfg) -> (mb2_render_config, keep_alive) or None
+    render: Callable = None
 
 
 def _cartpole_cfg(cfg):
@@ -66,6 +70,11 @@ def _room_init(w, cfg):
 def _room_objects():
     from .objects import room_objects
     return room_objects()
+
+
+def _room_render_cfg(cfg):
+    from .render_assets import make_render_config
+    return make_render_config(int(cfg.get("resolution", 64)), bool(cfg.get("rgbd", False)))
 
 
 SIMS: Dict[str, SimDesc] = {
@@ -104,6 +113,27 @@ SIMS: Dict[str, SimDesc] = {
                                   int(cfg.get("grab_period", 0))],
         defaults={"episode_len": 100, "seed": 0, "grab_period": 0},
         objects=_room_objects,
+    ),
+    # the room fixture built with -DROOM_ENABLE_RENDER=1 (BASELINE configs[3]); GPU only:
+    # the reference CPU backend cannot ray cast (src/render/ecs_system.cpp:684-689)
+    "room_render": SimDesc(
+        name="room_render",
+        sources=[os.path.join(_ROOT, "room", "sim.cpp")],
+        num_exports=17,
+        num_taskgraphs=1,
+        inputs=[Slot(0, "reset", "int32", (1,)), Slot(1, "action", "int32", (2, 3))],
+        outputs=[Slot(2, "reward", "float32", (2,)), Slot(3, "done", "int32", (2,)),
+                 Slot(6, "agent_pos", "float32", (2, 3)), Slot(7, "agent_rot", "float32", (2, 4)),
+                 Slot(8, "body_count", "int32", (1,)),
+                 Slot(9, "body_pos", "float32", (3,), dynamic=True),
+                 Slot(10, "body_rot", "float32", (4,), dynamic=True)],
+        pack_config=_room_cfg,
+        pack_init=_room_init,
+        oracle_extra=lambda cfg: [],
+        defaults={"episode_len": 100, "seed": 0, "grab_period": 0, "resolution": 64, "rgbd": False},
+        objects=_room_objects,
+        compile_flags=["-DROOM_ENABLE_RENDER=1"],
+        render=_room_render_cfg,
     ),
     "gridworld": SimDesc(
         name="gridworld",
@@ -177,7 +207,9 @@ def make_executor(name: str, num_worlds: int, gpu_id: int = 0, **cfg):
         numExportedBuffers=desc.num_exports,
     )
     compile_cfg = mb.CompileConfig(userSources=desc.sources,
-                                   userCompileFlags=["-I" + os.path.dirname(desc.sources[0])])
-    ex = mb.MWCudaExecutor(state, compile_cfg, gpu_id=gpu_id)
-    ex._keep_alive = keep_alive
+                                   userCompileFlags=["-I" + os.path.dirname(desc.sources[0])] +
+                                   list(desc.compile_flags))
+    render_cfg, render_keep = (desc.render(full) if desc.render is not None else (None, None))
+    ex = mb.MWCudaExecutor(state, compile_cfg, gpu_id=gpu_id, render_cfg=render_cfg)
+    ex._keep_alive = (keep_alive, render_keep)
     return ex

@@ -22,6 +22,9 @@ void Sim::registerTypes(ECSRegistry &registry, const Config &)
 {
     base::registerTypes(registry);
     PhysicsSystem::registerTypes(registry);
+#ifdef ROOM_ENABLE_RENDER
+    render::RenderingSystem::registerTypes(registry, nullptr);
+#endif
 
     registry.registerComponent<Action>();
     registry.registerComponent<Reward>();
@@ -52,6 +55,14 @@ void Sim::registerTypes(ECSRegistry &registry, const Config &)
     registry.exportColumn<PhysicsEntity, Rotation>((uint32_t)ExportID::BodyRot);
     registry.exportColumn<PhysicsEntity, Entity>((uint32_t)ExportID::BodyEntity);
     registry.exportColumn<PhysicsEntity, Velocity>((uint32_t)ExportID::BodyVel);
+#ifdef ROOM_ENABLE_RENDER
+    registry.exportColumn<render::RaycastOutputArchetype, render::RGBOutputBuffer>(
+        (uint32_t)ExportID::RenderRGB);
+    registry.exportColumn<render::RaycastOutputArchetype, render::DepthOutputBuffer>(
+        (uint32_t)ExportID::RenderDepth);
+    registry.exportColumn<PhysicsEntity, Scale>((uint32_t)ExportID::BodyScale);
+    registry.exportColumn<PhysicsEntity, ObjectID>((uint32_t)ExportID::BodyObject);
+#endif
 }
 
 static inline void setupBody(Engine &ctx, Entity e, Vector3 pos, Quat rot,
@@ -69,6 +80,9 @@ static inline void setupBody(Engine &ctx, Entity e, Vector3 pos, Quat rot,
     ctx.get<ExternalTorque>(e) = Vector3::zero();
     ctx.get<EntityType>(e) = type;
     ctx.get<broadphase::LeafID>(e) = PhysicsSystem::registerEntity(ctx, e, obj_id);
+#ifdef ROOM_ENABLE_RENDER
+    render::RenderingSystem::makeEntityRenderable(ctx, e);
+#endif
 }
 
 static inline void placeWall(Engine &ctx, Entity e, float x0, float x1,
@@ -348,6 +362,9 @@ void Sim::setupTasks(TaskGraphManager &mgr, const Config &)
     builder.addToGraph<ParallelForNode<Engine, lidarSystem,
         Entity, Position, Rotation, Lidar>>({obs});
 #endif
+#ifdef ROOM_ENABLE_RENDER
+    render::RenderingSystem::setupTasks(builder, {obs});
+#endif
 }
 
 Sim::Sim(Engine &ctx, const Config &cfg, const WorldInit &init)
@@ -380,6 +397,10 @@ Sim::Sim(Engine &ctx, const Config &cfg, const WorldInit &init)
         ctx.get<Reward>(agents[i]).v = 0.f;
         ctx.get<SelfObs>(agents[i]) = SelfObs {};
         ctx.get<Lidar>(agents[i]) = Lidar {};
+#ifdef ROOM_ENABLE_RENDER
+        render::RenderingSystem::attachEntityToView(ctx, agents[i], 90.f, 0.001f,
+                                                   Vector3 { 0.f, 0.f, 0.5f });
+#endif
     }
     ctx.singleton<WorldReset>().reset = 0;
     generateWorld(ctx);

@@ -15,6 +15,11 @@
 #include <madrona/components.hpp>
 #include <madrona/physics.hpp>
 #include <madrona/rand.hpp>
+#ifdef ROOM_ENABLE_RENDER
+// GPU-only build variant (BASELINE.json configs[3]): every body is renderable,
+// every agent carries a camera; the batch ray caster writes depth / RGB.
+#include <madrona/render/ecs.hpp>
+#endif
 
 namespace room {
 
@@ -51,6 +56,12 @@ enum class ExportID : uint32_t {
     BodyRot,
     BodyEntity,
     BodyVel,
+#ifdef ROOM_ENABLE_RENDER
+    RenderRGB,
+    RenderDepth,
+    BodyScale,
+    BodyObject,
+#endif
     NumExports,
 };
 
@@ -106,6 +117,19 @@ struct Lidar {
     LidarSample samples[kNumLidar];
 };
 
+#ifdef ROOM_ENABLE_RENDER
+struct Agent : public madrona::Archetype<
+    madrona::phys::RigidBody,
+    Action, Reward, Done, Progress, StepsRemaining, SelfObs, Lidar, EntityType,
+    madrona::render::Renderable, madrona::render::RenderCamera
+> {};
+
+struct PhysicsEntity : public madrona::Archetype<
+    madrona::phys::RigidBody,
+    EntityType,
+    madrona::render::Renderable
+> {};
+#else
 struct Agent : public madrona::Archetype<
     madrona::phys::RigidBody,
     Action, Reward, Done, Progress, StepsRemaining, SelfObs, Lidar, EntityType
@@ -115,6 +139,7 @@ struct PhysicsEntity : public madrona::Archetype<
     madrona::phys::RigidBody,
     EntityType
 > {};
+#endif
 
 struct Config {
     madrona::phys::ObjectManager *objMgr;
