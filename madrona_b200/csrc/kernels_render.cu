@@ -230,22 +230,16 @@ renderRaycastKernel(EngineState *Sp)
     const size_t bytes_per_view = (size_t)res * res * 4;
 
     __shared__ RenderInstance staged[kStagedInstances];
+    __shared__ RenderInstance stage_tmp[kStagedInstances];
+    __shared__ float stage_key[kStagedInstances];
+    __shared__ int stage_count[2];
 
     for (i32 v = blockIdx.y; v < num_views; v += gridDim.y) {
         const RenderView view = R.views[v];
         const i32 w = view.worldIDX;
-        const i32 num_inst = min(R.instanceCounts[w], kStagedInstances);
-        __syncthreads();
-        {
-            const u32 *src = (const u32 *)(R.instances + (size_t)w * R.maxInstancesPerWorld);
-            u32 *dst = (u32 *)staged;
-            const int words = num_inst * (int)(sizeof(RenderInstance) / 4);
-            for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-        }
-        __syncthreads();
-        if (!in_image) continue;
+        const i32 world_inst = min(R.instanceCounts[w], kStagedInstances);
 
-        // ---- primary ray (bvh_raycast.cpp:58-88)
+        // camera frame (shared by every pixel of the view)
         const Quat rot { view.rotation.w, view.rotation.x, view.rotation.y, view.rotation.z };
         const Vector3 ray_start { view.position.x, view.position.y, view.position.z };
         const Vector3 look_at = rot.inv().rotateVec({ 0, 1, 0 });
@@ -254,6 +248,65 @@ renderRaycastKernel(EngineState *Sp)
         const Vector3 forward = look_at.normalize();
         const Vector3 u = rot.inv().rotateVec({ 1, 0, 0 });
         const Vector3 vv = cross(forward, u).normalize();
+
+        // Stage the world's instances, keeping (in order) only those whose box
+        // touches the view frustum: no ray of this view could pass their slab
+        // test, so dropping them changes nothing but the work per ray.
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int k = threadIdx.x;
+            bool keep = false;
+            RenderInstance inst;
+            if (k < world_inst) {
+                inst = R.instances[(size_t)w * R.maxInstancesPerWorld + k];
+                keep = true;
+                const float hm = fabsf(h) * 1.02f + 0.01f;     // widened: conservative
+                const Vector3 normals[4] = { forward * hm - u, forward * hm + u,
+                                             forward * hm - vv, forward * hm + vv };
+                for (int pl = 0; pl < 4; pl++) {
+                    const Vector3 n = normals[pl];
+                    // box corner furthest along n
+                    const Vector3 far_corner {
+                        n.x >= 0 ? inst.aabbMax[0] : inst.aabbMin[0],
+                        n.y >= 0 ? inst.aabbMax[1] : inst.aabbMin[1],
+                        n.z >= 0 ? inst.aabbMax[2] : inst.aabbMin[2] };
+                    if (dot(far_corner - ray_start, n) < 0.f) keep = false;
+                }
+            }
+            const u32 kept = __ballot_sync(0xffffffffu, keep);
+            if (threadIdx.x == 0) stage_count[0] = __popc(kept);
+            if (threadIdx.x == 32) stage_count[1] = __popc(kept);
+            // near-to-far key: squared distance from the eye to the instance's box
+            // (0 inside).  Visiting near instances first shrinks t_max early, so
+            // the boxes of far instances fail their slab test instead of being
+            // entered.  Culled instances sort to the end.
+            float key = FLT_MAX;
+            if (keep) {
+                const float dx = fmaxf(fmaxf(inst.aabbMin[0] - ray_start.x, 0.f), ray_start.x - inst.aabbMax[0]);
+                const float dy = fmaxf(fmaxf(inst.aabbMin[1] - ray_start.y, 0.f), ray_start.y - inst.aabbMax[1]);
+                const float dz = fmaxf(fmaxf(inst.aabbMin[2] - ray_start.z, 0.f), ray_start.z - inst.aabbMax[2]);
+                key = dx * dx + dy * dy + dz * dz;
+            }
+            stage_key[k] = key;
+            stage_tmp[k] = inst;
+        }
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            // rank sort, ties broken by the original (engine) order
+            const int k = threadIdx.x;
+            const float mine = stage_key[k];
+            int rank = 0;
+            for (int j = 0; j < 64; j++) {
+                const float other = stage_key[j];
+                rank += (other < mine || (other == mine && j < k)) ? 1 : 0;
+            }
+            if (mine != FLT_MAX) staged[rank] = stage_tmp[k];
+        }
+        __syncthreads();
+        const i32 num_inst = stage_count[0] + stage_count[1];
+        if (!in_image) continue;
+
+        // ---- primary ray (bvh_raycast.cpp:58-88)
         const Vector3 horizontal = u * viewport;
         const Vector3 vertical = vv * viewport;
         const Vector3 lower_left = ray_start - horizontal / 2 - vertical / 2 + forward;

@@ -119,7 +119,17 @@ def render_depth(instances, meshes, verts, indices, cam_pos, cam_rot_inv, y_scal
         inv_d_w = (F(1) / d_w).astype(F)
     t_max = np.full((res, res), F(10000), dtype=F)
     hit = np.zeros((res, res), dtype=bool)
-    for inst in instances:
+
+    # the engine visits a view's instances near-to-far: squared distance from the
+    # eye to the instance's world box, ties in engine order (kernels_render.cu)
+    def eye_key(inst):
+        c = np.asarray(cam_pos, dtype=F)
+        lo, hi = np.asarray(inst["aabb_min"], F), np.asarray(inst["aabb_max"], F)
+        d = np.maximum(np.maximum(lo - c, F(0)), c - hi).astype(F)
+        return float((d[0] * d[0] + d[1] * d[1] + d[2] * d[2]).astype(F))
+
+    order = sorted(range(len(instances)), key=lambda i: (eye_key(instances[i]), i))
+    for inst in (instances[i] for i in order):
         ok = _slab(np.asarray(inst["aabb_min"], F), np.asarray(inst["aabb_max"], F), o_w, inv_d_w, t_max)
         if not ok.any():
             continue
