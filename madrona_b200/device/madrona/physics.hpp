@@ -527,31 +527,55 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
 {
     math::Diag3x3 inv_d = math::Diag3x3::fromVec(d).inv();
 
+    // Two-phase traversal: every lane first walks the tree up to its next
+    // entered leaf, then the lanes that called together run the (expensive)
+    // leaf test together.  The warp votes keep the compiler from folding the
+    // two phases back into one divergent loop (a few lanes at a time in the
+    // leaf test).  Per ray the visit order -- and so every float -- is the
+    // reference's (src/physics/broadphase.cpp traceRay: pop node, children
+    // 0..3 in order).
+    const unsigned peers = __activemask();
     int32_t stack[32];
-    stack[0] = 0;
-    CountT stack_size = 1;
+    CountT stack_size = 0;
+    int32_t cur = 0;
+    int cur_child = 0;
+    bool walking = true;
     Entity closest = Entity::none();
     math::Vector3 closest_normal { 0, 0, 0 };
 
-    while (stack_size > 0) {
-        const mb2::BVHNode &node = s_.nodes[stack[--stack_size]];
-        for (int i = 0; i < 4; i++) {
+    while (__any_sync(peers, walking)) {
+        int32_t leaf_idx = -1;
+        while (walking) {
+            if (cur_child == 4) {
+                if (stack_size == 0) {
+                    walking = false;
+                    break;
+                }
+                cur = stack[--stack_size];
+                cur_child = 0;
+            }
+            const mb2::BVHNode &node = s_.nodes[cur];
+            const int i = cur_child++;
             int32_t child = node.children[i];
             if (child == -1) continue;
             math::AABB box { { node.minX[i], node.minY[i], node.minZ[i] },
                              { node.maxX[i], node.maxY[i], node.maxZ[i] } };
             if (!box.rayIntersects(o, inv_d, 0.f, t_max)) continue;
             if (child & 0x80000000) {
-                int32_t leaf_idx = child & 0x7fffffff;
-                float hit_t;
-                math::Vector3 leaf_normal;
-                if (traceRayIntoLeaf(leaf_idx, o, d, 0.f, t_max, &hit_t, &leaf_normal)) {
-                    t_max = hit_t;
-                    closest = unpackEntity(s_.leafEntities[leaf_idx]);
-                    closest_normal = leaf_normal;
-                }
-            } else {
-                stack[stack_size++] = child;
+                leaf_idx = child & 0x7fffffff;
+                break;
+            }
+            stack[stack_size++] = child;
+        }
+        __syncwarp(peers);
+
+        if (leaf_idx >= 0) {
+            float hit_t;
+            math::Vector3 leaf_normal;
+            if (traceRayIntoLeaf(leaf_idx, o, d, 0.f, t_max, &hit_t, &leaf_normal)) {
+                t_max = hit_t;
+                closest = unpackEntity(s_.leafEntities[leaf_idx]);
+                closest_normal = leaf_normal;
             }
         }
     }
