@@ -756,6 +756,7 @@ __device__ HullInWorld placeHull(const PHalfEdgeMesh &mesh, Vector3 t, Quat r, D
 
     Vector3 center = Vector3::zero();
     const u32 nv = mesh.numVertices;
+#pragma unroll 1
     for (u32 i = 0; i < nv; i++) {
         Vector3 p = vert_m * mesh.vertices[i] + t;
         verts[i] = p;
@@ -764,6 +765,7 @@ __device__ HullInWorld placeHull(const PHalfEdgeMesh &mesh, Vector3 t, Quat r, D
     center /= (float)nv;
 
     const u32 nf = mesh.numFaces;
+#pragma unroll 1
     for (u32 i = 0; i < nf; i++) {
         PPlane local = mesh.facePlanes[i];
         Vector3 on_plane = vert_m * (local.normal * local.d) + t;
@@ -781,6 +783,7 @@ __device__ __forceinline__ float planeDistance(const PPlane &pl, Vector3 p)
 __device__ float hullSupportDistance(const PPlane &pl, const HullInWorld &h)
 {
     float lowest = FLT_MAX;
+#pragma unroll 1
     for (u32 i = 0; i < h.numVerts; i++) {
         float along = dot(h.verts[i], pl.normal);
         if (along < lowest) lowest = along;
@@ -882,6 +885,7 @@ __device__ i32 mostOpposedFace(const HullInWorld &h, Vector3 ref_normal)
 {
     float lowest = FLT_MAX;
     i32 face = -1;
+#pragma unroll 1
     for (u32 f = 0; f < h.numFaces; f++) {
         float d = dot(h.planes[f].normal, ref_normal);
         if (d < lowest) {
@@ -893,11 +897,12 @@ __device__ i32 mostOpposedFace(const HullInWorld &h, Vector3 ref_normal)
 }
 
 // Sutherland-Hodgman against one plane; "<= 0" is inside (narrowphase.cpp:617-652)
-__device__ int clipAgainst(Vector3 *dst, const PPlane &pl, const Vector3 *src, int n)
+__device__ __noinline__ int clipAgainst(Vector3 *dst, const PPlane &pl, const Vector3 *src, int n)
 {
     int m = 0;
     Vector3 v1 = src[n - 1];
     float d1 = planeDistance(pl, v1);
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
         Vector3 v2 = src[i];
         float d2 = planeDistance(pl, v2);
@@ -926,7 +931,7 @@ struct ManifoldOut {
 // (largest |area| with AB), Q (most negative area outside ABC)
 // (narrowphase.cpp:771-879).  World offset / frame are identity in the only
 // live call sites.
-__device__ ManifoldOut reduceManifold(Vector3 normal, const Vector3 *pts, const float *depths, int n)
+__device__ __noinline__ ManifoldOut reduceManifold(Vector3 normal, const Vector3 *pts, const float *depths, int n)
 {
     ManifoldOut m;
     m.normal = normal;
@@ -947,6 +952,7 @@ __device__ ManifoldOut reduceManifold(Vector3 normal, const Vector3 *pts, const 
     m.depths[0] = depths[0];
 
     float far2 = 0.f;
+#pragma unroll 1
     for (int i = 1; i < n; i++) {
         float d2 = m.points[0].distance2(pts[i]);
         if (d2 > far2) {
@@ -961,6 +967,7 @@ __device__ ManifoldOut reduceManifold(Vector3 normal, const Vector3 *pts, const 
     // NB: the reference stores this sign in a bool, so "-1" never compares
     // equal and the winding flip below never fires; kept for parity.
     bool best_sign = false;
+#pragma unroll 1
     for (int i = 1; i < n; i++) {
         Vector3 bc = pts[i] - m.points[1];
         float signed_area = normal.dot(cross(ba, bc));
@@ -982,6 +989,7 @@ __device__ ManifoldOut reduceManifold(Vector3 normal, const Vector3 *pts, const 
     Vector3 cb = m.points[2] - m.points[1];
     Vector3 ac = m.points[0] - m.points[2];
     float most_neg = 0.f;
+#pragma unroll 1
     for (int i = 1; i < n; i++) {
         Vector3 aq = m.points[0] - pts[i];
         Vector3 qc = pts[i] - m.points[2];
@@ -1041,6 +1049,7 @@ __device__ ManifoldOut faceFaceManifold(const PPlane &ref_plane, i32 ref_face, i
     // keep what is at or below the reference plane, projected onto it
     float depths[kClipCap];
     int kept = 0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
         Vector3 p = src[i];
         float d = planeDistance(ref_plane, p);
@@ -1257,7 +1266,12 @@ __device__ __forceinline__ T warpBroadcast(T v, int src)
 }
 
 // (separation, index) of the element the sequential scan would have kept.
-__device__ __forceinline__ void warpSequentialWinner(float &sep, i32 &idx, bool have)
+struct Winner {
+    float sep;
+    i32 idx;
+};
+
+__device__ __noinline__ Winner warpSequentialWinnerImpl(float sep, i32 idx, bool have)
 {
     const u32 positives = __ballot_sync(0xffffffffu, have && sep > 0.f);
     if (positives) {
@@ -1270,9 +1284,7 @@ __device__ __forceinline__ void warpSequentialWinner(float &sep, i32 &idx, bool 
         }
         const u32 owner = __ballot_sync(0xffffffffu, have && sep > 0.f && idx == cand);
         const int src = __ffs(owner) - 1;
-        sep = __shfl_sync(0xffffffffu, sep, src);
-        idx = cand;
-        return;
+        return Winner { __shfl_sync(0xffffffffu, sep, src), cand };
     }
     float s = have ? sep : -FLT_MAX;
     i32 k = have ? idx : 0x7fffffff;
@@ -1284,8 +1296,14 @@ __device__ __forceinline__ void warpSequentialWinner(float &sep, i32 &idx, bool 
             k = ok;
         }
     }
-    sep = s;
-    idx = k;
+    return Winner { s, k };
+}
+
+__device__ __forceinline__ void warpSequentialWinner(float &sep, i32 &idx, bool have)
+{
+    const Winner w = warpSequentialWinnerImpl(sep, idx, have);
+    sep = w.sep;
+    idx = w.idx;
 }
 
 // Executed by ALL lanes for the hull-hull candidate owned by lane `src`.
@@ -1311,10 +1329,12 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
         const Mat3x3 rot_a = Mat3x3::fromQuat(ps.aRot), rot_b = Mat3x3::fromQuat(ps.bRot);
         const Mat3x3 vm_a = rot_a * ps.aScale, vm_b = rot_b * ps.bScale;
         const Mat3x3 nm_a = rot_a * ps.aScale.inv(), nm_b = rot_b * ps.bScale.inv();
+#pragma unroll 1
         for (u32 i = lane; i < nva + nvb; i += 32) {
             if (i < nva) verts_a[i] = vm_a * am.vertices[i] + ps.aPos;
             else verts_b[i - nva] = vm_b * bm.vertices[i - nva] + ps.bPos;
         }
+#pragma unroll 1
         for (u32 i = lane; i < nfa + nfb; i += 32) {
             const bool is_a = i < nfa;
             const PPlane local = is_a ? am.facePlanes[i] : bm.facePlanes[i - nfa];
@@ -1328,6 +1348,7 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
     __syncwarp();
     // centres: vertex sums in index order (float addition is not associative)
     Vector3 center_a = Vector3::zero();
+#pragma unroll 1
     for (u32 i = 0; i < nva; i++) center_a += verts_a[i];
     center_a /= (float)nva;
 
@@ -1349,6 +1370,7 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
     float e_sep = -FLT_MAX;
     i32 e_pair = 0x7fffffff;
     Vector3 e_normal = Vector3::zero();
+#pragma unroll 1
     for (u32 p = lane; p < ea * eb; p += 32) {
         const u32 ha = (p / eb) * 2, hb = (p % eb) * 2;
         const PHalfEdge a0 = am.halfEdges[ha];
@@ -2008,14 +2030,13 @@ __device__ __forceinline__ void forEachWorldBody(const EngineState &S, const Phy
     }
 }
 
-// Neighbouring phases that share the warp-per-world mapping are fused into one
-// launch (flags): integrate -> narrowphase, and position solve -> velocity
-// update -> velocity solve.  Inside a world only __syncwarp is needed.
-constexpr u32 kFuseIntegrate = 1u, kFuseSetVelocities = 2u, kFuseSolveVelocities = 4u;
-
-template <u32 OP, int MINB>
-__global__ void __launch_bounds__(32 * kPhysWarps, MINB)
-physWorldKernel(EngineState *Sp, u32 flags)
+// One warp per world; kPhysWarps worlds per block.  (Fusing neighbouring phases
+// into one launch -- integrate -> narrowphase, position solve -> velocity update
+// -> velocity solve -- was measured: no gain, and the bigger kernels miss the
+// 32 KB instruction cache more)
+template <u32 OP>
+__global__ void __launch_bounds__(32 * kPhysWarps, 8)
+physWorldKernel(EngineState *Sp)
 {
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
@@ -2028,25 +2049,9 @@ physWorldKernel(EngineState *Sp, u32 flags)
         phaseFindCandidates(S, P, w, lane, warp, cand_scratch);
     } else if constexpr (OP == PhaseNarrowphase) {
         __shared__ LevelScratch scratch;
-        if (flags & kFuseIntegrate) {
-            forEachWorldBody(S, P, w, lane, [&](const BodyArchetype &b, i32 row) {
-                rowIntegrate(S, P, b, row, w);
-            });
-            __syncwarp();
-        }
         phaseNarrowphase(S, P, w, lane, warp, scratch);
     } else if constexpr (OP == PhaseSolvePositions) {
         phaseSolvePositions(S, P, w, lane);
-        if (flags & kFuseSetVelocities) {
-            __syncwarp();
-            forEachWorldBody(S, P, w, lane, [&](const BodyArchetype &b, i32 row) {
-                rowSetVelocity(S, P, b, row, w);
-            });
-        }
-        if (flags & kFuseSolveVelocities) {
-            __syncwarp();
-            phaseSolveVelocities(S, P, w, lane);
-        }
     } else if constexpr (OP == PhaseSolveVelocities) {
         phaseSolveVelocities(S, P, w, lane);
     }
@@ -2148,16 +2153,6 @@ static dim3 bodyGrid(Executor *ex)
     return dim3((unsigned)std::max(blocks, 1), std::max(P.numBodyArchetypes, 1u));
 }
 
-// min-blocks-per-SM variant of the per-world kernels (register budget =
-// 65536 / (64 * MINB)): 8 -> 128 regs, 12 -> 85, 16 -> 64
-template <u32 OP>
-static void launchWorld(int minb, unsigned grid, unsigned block, cudaStream_t s, EngineState *d, u32 flags)
-{
-    if (minb >= 16) physWorldKernel<OP, 16><<<grid, block, 0, s>>>(d, flags);
-    else if (minb >= 12) physWorldKernel<OP, 12><<<grid, block, 0, s>>>(d, flags);
-    else physWorldKernel<OP, 8><<<grid, block, 0, s>>>(d, flags);
-}
-
 bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, cudaStream_t s,
                          std::string *err)
 {
@@ -2171,17 +2166,8 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
     const unsigned wgrid = (W + kPhysWarps - 1) / kPhysWarps;
     const unsigned wblock = 32 * kPhysWarps;
     const dim3 bgrid = bodyGrid(ex);
-    // which neighbouring phases share a launch (measured on B200: see DESIGN.md)
-    const u32 fuse = (u32)envU64p("MADRONA_B200_PHYS_FUSE", 0);
-    const int mb_cand = (int)envU64p("MADRONA_B200_MINB_CAND", 8);
-    const int mb_narrow = (int)envU64p("MADRONA_B200_MINB_NARROW", 8);
-    const int mb_pos = (int)envU64p("MADRONA_B200_MINB_POS", 8);
-    const int mb_vel = (int)envU64p("MADRONA_B200_MINB_VEL", 8);
     for (uint32_t i = 0; i < count; i++) {
         const NodeRecord &rec = recs[i];
-        auto nextIs = [&](uint32_t ahead, u32 kind) {
-            return i + ahead < count && recs[i + ahead].kind == kind;
-        };
         switch (rec.kind) {
         case NodePhysBroadphaseUpdate:
             // tag 0 (post-integration) never rebuilds in the reference either; a
@@ -2194,39 +2180,22 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
             // joints are iterated per world by the solver: keep their table in
             // world order (the reference sorts Joint here too, xpbd.cpp:1092-1096)
             launchSortArchetype(ex, ph->hPhys.jointArchetype, 1, s);
-            launchWorld<PhaseFindCandidates>(mb_cand, wgrid, wblock, s, d, 0u);
+            physWorldKernel<PhaseFindCandidates><<<wgrid, wblock, 0, s>>>(d);
             break;
         case NodePhysSubstepBegin:
-            if ((fuse & 1u) && nextIs(1, NodePhysNarrowphase)) {
-                launchWorld<PhaseNarrowphase>(mb_narrow, wgrid, wblock, s, d, kFuseIntegrate);
-                i += 1;
-            } else {
-                physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
-            }
+            physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysNarrowphase:
-            launchWorld<PhaseNarrowphase>(mb_narrow, wgrid, wblock, s, d, 0u);
+            physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d);
             break;
-        case NodePhysSolvePositions: {
-            u32 flags = 0;
-            uint32_t skip = 0;
-            if ((fuse & 2u) && nextIs(1, NodePhysSetVelocities)) {
-                flags |= kFuseSetVelocities;
-                skip = 1;
-                if ((fuse & 4u) && nextIs(2, NodePhysSolveVelocities)) {
-                    flags |= kFuseSolveVelocities;
-                    skip = 2;
-                }
-            }
-            launchWorld<PhaseSolvePositions>(mb_pos, wgrid, wblock, s, d, flags);
-            i += skip;
+        case NodePhysSolvePositions:
+            physWorldKernel<PhaseSolvePositions><<<wgrid, wblock, 0, s>>>(d);
             break;
-        }
         case NodePhysSetVelocities:
             physBodyKernel<PhaseSetVelocities><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysSolveVelocities:
-            launchWorld<PhaseSolveVelocities>(mb_vel, wgrid, wblock, s, d, 0u);
+            physWorldKernel<PhaseSolveVelocities><<<wgrid, wblock, 0, s>>>(d);
             break;
         default:
             *err = "unknown physics node kind " + std::to_string(rec.kind);
