@@ -529,38 +529,78 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
 
     // Two-phase traversal: every lane first walks the tree up to its next
     // entered leaf, then the lanes that called together run the (expensive)
-    // leaf test together.  The warp votes keep the compiler from folding the
-    // two phases back into one divergent loop (a few lanes at a time in the
-    // leaf test).  Per ray the visit order -- and so every float -- is the
-    // reference's (src/physics/broadphase.cpp traceRay: pop node, children
-    // 0..3 in order).
+    // leaf test together; the warp votes keep the compiler from folding the
+    // two phases back into one divergent loop.
+    //
+    // Walking is latency bound, so a popped node is read once, whole (28
+    // independent loads), and its four slab tests run side by side.  The
+    // reference tests child i against the t_max current at that moment
+    // (src/physics/broadphase.cpp traceRay + math.inl:1698-1735); that test
+    // factors exactly into a part independent of t_max (the slab intervals
+    // overlap) and "t_max > entry distance", so the first part is evaluated at
+    // pop time and the second when the child's turn comes: same decisions, same
+    // visit order (pop node, children 0..3 in order), same floats.
     const unsigned peers = __activemask();
     int32_t stack[32];
-    CountT stack_size = 0;
-    int32_t cur = 0;
-    int cur_child = 0;
+    stack[0] = 0;
+    CountT stack_size = 1;
+    unsigned pending = 0;                 // slots of the current node still to visit
+    int32_t kid0 = -1, kid1 = -1, kid2 = -1, kid3 = -1;
+    float ent0 = 0.f, ent1 = 0.f, ent2 = 0.f, ent3 = 0.f;
     bool walking = true;
     Entity closest = Entity::none();
     math::Vector3 closest_normal { 0, 0, 0 };
 
+    auto slab = [&](const mb2::BVHNode &node, int i, float *entry) {
+        float t_near = 0.f, t_far = INFINITY;
+        bool overlap = true;
+        {
+            float t0 = (node.minX[i] - o.x) * inv_d.d0, t1 = (node.maxX[i] - o.x) * inv_d.d0;
+            if (inv_d.d0 < 0.f) { float t = t0; t0 = t1; t1 = t; }
+            t_near = t0 > t_near ? t0 : t_near;
+            t_far = t1 < t_far ? t1 : t_far;
+            overlap = overlap && !(t_far <= t_near);
+        }
+        {
+            float t0 = (node.minY[i] - o.y) * inv_d.d1, t1 = (node.maxY[i] - o.y) * inv_d.d1;
+            if (inv_d.d1 < 0.f) { float t = t0; t0 = t1; t1 = t; }
+            t_near = t0 > t_near ? t0 : t_near;
+            t_far = t1 < t_far ? t1 : t_far;
+            overlap = overlap && !(t_far <= t_near);
+        }
+        {
+            float t0 = (node.minZ[i] - o.z) * inv_d.d2, t1 = (node.maxZ[i] - o.z) * inv_d.d2;
+            if (inv_d.d2 < 0.f) { float t = t0; t0 = t1; t1 = t; }
+            t_near = t0 > t_near ? t0 : t_near;
+            t_far = t1 < t_far ? t1 : t_far;
+            overlap = overlap && !(t_far <= t_near);
+        }
+        *entry = t_near;
+        return overlap;
+    };
+
     while (__any_sync(peers, walking)) {
         int32_t leaf_idx = -1;
         while (walking) {
-            if (cur_child == 4) {
+            if (pending == 0) {
                 if (stack_size == 0) {
                     walking = false;
                     break;
                 }
-                cur = stack[--stack_size];
-                cur_child = 0;
+                const mb2::BVHNode &node = s_.nodes[stack[--stack_size]];
+                kid0 = node.children[0]; kid1 = node.children[1];
+                kid2 = node.children[2]; kid3 = node.children[3];
+                const bool in0 = slab(node, 0, &ent0), in1 = slab(node, 1, &ent1);
+                const bool in2 = slab(node, 2, &ent2), in3 = slab(node, 3, &ent3);
+                pending = ((kid0 != -1 && in0) ? 1u : 0u) | ((kid1 != -1 && in1) ? 2u : 0u) |
+                          ((kid2 != -1 && in2) ? 4u : 0u) | ((kid3 != -1 && in3) ? 8u : 0u);
+                continue;
             }
-            const mb2::BVHNode &node = s_.nodes[cur];
-            const int i = cur_child++;
-            int32_t child = node.children[i];
-            if (child == -1) continue;
-            math::AABB box { { node.minX[i], node.minY[i], node.minZ[i] },
-                             { node.maxX[i], node.maxY[i], node.maxZ[i] } };
-            if (!box.rayIntersects(o, inv_d, 0.f, t_max)) continue;
+            const int i = __ffs((int)pending) - 1;
+            pending &= pending - 1;
+            const float entry = i == 0 ? ent0 : (i == 1 ? ent1 : (i == 2 ? ent2 : ent3));
+            const int32_t child = i == 0 ? kid0 : (i == 1 ? kid1 : (i == 2 ? kid2 : kid3));
+            if (t_max <= entry) continue;
             if (child & 0x80000000) {
                 leaf_idx = child & 0x7fffffff;
                 break;

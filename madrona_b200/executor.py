@@ -82,7 +82,8 @@ class _RenderConfigC(ctypes.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_PKG_DIR, "libmadrona_b200.so")
+    # MADRONA_B200_LIB: an alternative build of the same library (A/B measurements)
+    return os.environ.get("MADRONA_B200_LIB") or os.path.join(_PKG_DIR, "libmadrona_b200.so")
 
 
 def load_library() -> ctypes.CDLL:
