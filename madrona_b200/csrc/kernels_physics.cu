@@ -931,7 +931,7 @@ struct ManifoldOut {
 // (largest |area| with AB), Q (most negative area outside ABC)
 // (narrowphase.cpp:771-879).  World offset / frame are identity in the only
 // live call sites.
-__device__ __noinline__ ManifoldOut reduceManifold(Vector3 normal, const Vector3 *pts, const float *depths, int n)
+__device__ __noinline__ ManifoldOut reduceManifoldLarge(Vector3 normal, const Vector3 *pts, const float *depths, int n)
 {
     ManifoldOut m;
     m.normal = normal;
@@ -1006,6 +1006,21 @@ __device__ __noinline__ ManifoldOut reduceManifold(Vector3 normal, const Vector3
     if (far2 == 0.f || best_area == 0.f || most_neg == 0.f) {
         m.count = 0;
         m.normal = Vector3::zero();
+    }
+    return m;
+}
+
+// the common case (a box face resting on something: <= 4 points) stays inline
+__device__ __forceinline__ ManifoldOut reduceManifold(Vector3 normal, const Vector3 *pts, const float *depths, int n)
+{
+    if (n > 4) return reduceManifoldLarge(normal, pts, depths, n);
+    ManifoldOut m;
+    m.normal = normal;
+    m.count = n;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        m.points[i] = i < n ? pts[i] : Vector3::zero();
+        m.depths[i] = i < n ? depths[i] : 0.f;
     }
     return m;
 }
@@ -1222,20 +1237,54 @@ __device__ bool narrowphaseSimple(EngineState &S, const PairSetup &ps, Contact &
         return true;
     }
     case 6: {   // plane is b and the reference
+        // The hull is never stored: every world-space vertex / face normal is
+        // produced where it is consumed, with placeHull's per-element formulas
+        // (vertex = R S v + t, normal = normalize(R S^-1 n)).
         const PHalfEdgeMesh &am = ps.aPrim->hull;
-        if (am.numVertices > (u32)kMaxHullVerts || am.numFaces > (u32)kMaxHullFaces) {
-            atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
-            return false;
-        }
-        Vector3 verts[kMaxHullVerts];
-        PPlane planes[kMaxHullFaces];
-        Vector3 clip[kClipCap];
-        HullInWorld a = placeHull(am, ps.aPos, ps.aRot, ps.aScale, verts, planes);
+        const Mat3x3 rot = Mat3x3::fromQuat(ps.aRot);
+        const Mat3x3 vert_m = rot * ps.aScale;
+        const Mat3x3 norm_m = rot * ps.aScale.inv();
         const Vector3 n = ps.bRot.rotateVec(Vector3 { 0, 0, 1 });
         const PPlane plane { n, dot(n, ps.bPos) };
-        if (hullSupportDistance(plane, a) > 0.0f) return false;
-        const i32 inc_face = mostOpposedFace(a, plane.normal);
-        ManifoldOut m = facePlaneManifold(plane, inc_face, a, clip);
+
+        float lowest = FLT_MAX;                       // hullSupportDistance
+#pragma unroll 2
+        for (u32 i = 0; i < am.numVertices; i++) {
+            const Vector3 p = vert_m * am.vertices[i] + ps.aPos;
+            const float along = dot(p, plane.normal);
+            if (along < lowest) lowest = along;
+        }
+        if (lowest - plane.d > 0.0f) return false;
+
+        float most = FLT_MAX;                         // mostOpposedFace
+        i32 inc_face = -1;
+#pragma unroll 2
+        for (u32 f = 0; f < am.numFaces; f++) {
+            const Vector3 face_n = (norm_m * am.facePlanes[f].normal).normalize();
+            const float d = dot(face_n, plane.normal);
+            if (d < most) {
+                most = d;
+                inc_face = (i32)f;
+            }
+        }
+
+        Vector3 clip[kClipCap];                       // facePlaneManifold
+        float depths[kClipCap];
+        int kept = 0;
+        u32 he = am.faceBaseHalfEdges[inc_face];
+        const u32 start = he;
+        do {
+            const PHalfEdge cur = am.halfEdges[he];
+            he = cur.next;
+            const Vector3 p = vert_m * am.vertices[cur.rootVertex] + ps.aPos;
+            const float d = planeDistance(plane, p);
+            if (d <= 0.0f && kept < kClipCap) {
+                clip[kept] = p - d * plane.normal;
+                depths[kept] = -d;
+                kept++;
+            }
+        } while (he != start);
+        ManifoldOut m = reduceManifold(plane.normal, clip, depths, kept);
         if (m.count <= 0) return false;
         writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, m);
         return true;
