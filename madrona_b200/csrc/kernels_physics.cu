@@ -175,6 +175,40 @@ __device__ __forceinline__ Vector3 mulDiag(Vector3 d, Vector3 v)
     return Vector3 { d.x * v.x, d.y * v.y, d.z * v.z };
 }
 
+// Wide accesses for the 16 / 24 / 40-byte row types (columns are 256-byte
+// aligned, BVH arrays 128-byte aligned): one request per 8 or 16 bytes instead
+// of one per float -- the row kernels are LSU-queue bound otherwise.
+__device__ __forceinline__ Quat loadQuat(const Quat *p)
+{
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    return Quat { v.x, v.y, v.z, v.w };
+}
+
+__device__ __forceinline__ void storeQuat(Quat *p, Quat q)
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(q.w, q.x, q.y, q.z);
+}
+
+template <typename T>
+__device__ __forceinline__ T loadPairs(const T *p)
+{
+    static_assert(sizeof(T) % 8 == 0, "");
+    union { T t; float2 v[sizeof(T) / 8]; } u;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 8); i++) u.v[i] = reinterpret_cast<const float2 *>(p)[i];
+    return u.t;
+}
+
+template <typename T>
+__device__ __forceinline__ void storePairs(T *p, const T &value)
+{
+    static_assert(sizeof(T) % 8 == 0, "");
+    union U { T t; float2 v[sizeof(T) / 8]; __device__ U() {} } u;
+    u.t = value;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 8); i++) reinterpret_cast<float2 *>(p)[i] = u.v[i];
+}
+
 __device__ __forceinline__ float atomicMinFloat(float *addr, float value)
 {
     float old = *(volatile float *)addr;
@@ -226,7 +260,7 @@ __device__ __forceinline__ void rowUpdateLeaf(const EngineState &S, const Physic
 
         const i32 leaf = bodyCol<i32>(S, b, PCLeafID, row);
         const Vector3 pos = bodyCol<Vector3>(S, b, PCPosition, row);
-        const Quat rot = bodyCol<Quat>(S, b, PCRotation, row);
+        const Quat rot = loadQuat(&bodyCol<Quat>(S, b, PCRotation, row));
         const Diag3x3 scale = bodyCol<Diag3x3>(S, b, PCScale, row);
         const i32 obj = bodyCol<i32>(S, b, PCObjectID, row);
         const Vector3 lin_vel = bodyCol<PVelocity>(S, b, PCVelocity, row).linear;
@@ -236,10 +270,10 @@ __device__ __forceinline__ void rowUpdateLeaf(const EngineState &S, const Physic
 
         PAABB out { { grown.pMin.x, grown.pMin.y, grown.pMin.z },
                     { grown.pMax.x, grown.pMax.y, grown.pMax.z } };
-        bvh.leafAABBs[leaf] = out;
+        storePairs(&bvh.leafAABBs[leaf], out);
         LeafTransform lt { { pos.x, pos.y, pos.z }, { rot.w, rot.x, rot.y, rot.z },
                            { scale.d0, scale.d1, scale.d2 } };
-        bvh.leafTransforms[leaf] = lt;
+        storePairs(&bvh.leafTransforms[leaf], lt);
         bvh.sortedLeaves[leaf] = leaf;
     }
 }
@@ -649,8 +683,8 @@ __device__ __forceinline__ void rowIntegrate(const EngineState &S, const Physics
     {
 
         Vector3 x = bodyCol<Vector3>(S, b, PCPosition, row);
-        Quat q = bodyCol<Quat>(S, b, PCRotation, row);
-        const PVelocity vel = bodyCol<PVelocity>(S, b, PCVelocity, row);
+        Quat q = loadQuat(&bodyCol<Quat>(S, b, PCRotation, row));
+        const PVelocity vel = loadPairs(&bodyCol<PVelocity>(S, b, PCVelocity, row));
         Vector3 v = vel.linear;
         Vector3 omega = vel.angular;
         const u32 resp = bodyCol<u32>(S, b, PCResponseType, row);
@@ -664,8 +698,7 @@ __device__ __forceinline__ void rowIntegrate(const EngineState &S, const Physics
         if (resp == kRespStatic) {
             pre_pos.x = x;
             pre_pos.q = q;
-            pre_vel.linear = Vector3::zero();
-            pre_vel.angular = Vector3::zero();
+            storePairs(&pre_vel, PVelocity { Vector3::zero(), Vector3::zero() });
             return;
         }
 
@@ -699,11 +732,10 @@ __device__ __forceinline__ void rowIntegrate(const EngineState &S, const Physics
         q = q.normalize();
 
         bodyCol<Vector3>(S, b, PCPosition, row) = x;
-        bodyCol<Quat>(S, b, PCRotation, row) = q;
+        storeQuat(&bodyCol<Quat>(S, b, PCRotation, row), q);
         pre_pos.x = x;
         pre_pos.q = q;
-        pre_vel.linear = v;
-        pre_vel.angular = omega;
+        storePairs(&pre_vel, PVelocity { v, omega });
     }
 }
 
@@ -712,7 +744,7 @@ __device__ __forceinline__ void rowSetVelocity(const EngineState &S, const Physi
     {
         const float h = worldParams(S, P, w).h;
         const Vector3 x = bodyCol<Vector3>(S, b, PCPosition, row);
-        const Quat q = bodyCol<Quat>(S, b, PCRotation, row);
+        const Quat q = loadQuat(&bodyCol<Quat>(S, b, PCRotation, row));
         const PPosRot prev = bodyCol<PPosRot>(S, b, PCPrevState, row);
 
         // bitwise-equal orientations mean exactly zero angular velocity
@@ -727,7 +759,7 @@ __device__ __forceinline__ void rowSetVelocity(const EngineState &S, const Physi
         PVelocity out;
         out.linear = (x - prev.x) / h;
         out.angular = dq.w > 0.f ? new_omega : -new_omega;
-        bodyCol<PVelocity>(S, b, PCVelocity, row) = out;
+        storePairs(&bodyCol<PVelocity>(S, b, PCVelocity, row), out);
     }
 }
 
@@ -2083,8 +2115,13 @@ __device__ __forceinline__ void forEachWorldBody(const EngineState &S, const Phy
 // into one launch -- integrate -> narrowphase, position solve -> velocity update
 // -> velocity solve -- was measured: no gain, and the bigger kernels miss the
 // 32 KB instruction cache more)
+#ifndef MB2_NARROW_MINB
+#define MB2_NARROW_MINB 8
+#endif
+constexpr int physMinBlocks(u32 op) { return op == 6u /* PhaseNarrowphase */ ? MB2_NARROW_MINB : 8; }
+
 template <u32 OP>
-__global__ void __launch_bounds__(32 * kPhysWarps, 8)
+__global__ void __launch_bounds__(32 * kPhysWarps, physMinBlocks(OP))
 physWorldKernel(EngineState *Sp)
 {
     EngineState &S = *Sp;

@@ -1,8 +1,9 @@
 #!/bin/bash
-# A/B two builds of libmadrona_b200 on one box: scripts/ab_bench.sh libA.so libB.so [bench args...]
-A=$1; B=$2; shift 2
+# Compare builds of libmadrona_b200 on one box (same clocks, same run):
+#   scripts/ab_bench.sh "libA.so libB.so ..." [bench args...]
+LIBS=$1; shift
 for rep in 1 2; do
-  for lib in "$A" "$B"; do
+  for lib in $LIBS; do
     MADRONA_B200_LIB=$lib python bench.py --no-cpu-baseline "$@" 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
