@@ -1892,27 +1892,76 @@ __device__ void solveJoint(EngineState &S, const PhysicsState &P, const PObjectM
     q2_ref = q2;
 }
 
-// One warp per world.  Contacts are swept level by level (Contact::level): the
-// lanes of a level run concurrently, levels run in order -- same floats as the
-// reference's one-thread-per-world sequential sweep (xpbd.cpp:720-736), a
-// fraction of its latency.  Joints follow sequentially.
-__device__ void phaseSolvePositions(EngineState &S, const PhysicsState &P, const i32 w, const int lane)
+// Contact sweep of one world by a group of LPW lanes (32 / LPW worlds share a
+// warp).  Contacts are swept level by level (Contact::level): the contacts of a
+// level run concurrently, levels run in order -- same floats as the reference's
+// one-thread-per-world sequential sweep (xpbd.cpp:720-736).  Contacts are taken
+// in chunks of 32, chunk-major: a later chunk only holds later contacts and the
+// levels inside a chunk run in order, so any two contacts sharing a mutable body
+// keep their sequential order.  Inside a level the members are compacted onto
+// the group's first lanes (ballot + find-nth-set).
+// The solves are latency bound with ~4 contacts per level, so two worlds per
+// warp multiplies the worlds in flight per SM at no register cost (measured on B200, room
+// 8192 worlds: 32 lanes/world 1.103 ms/step, 16: 1.097, 8: 1.080).
+#ifndef MB2_SOLVER_LPW
+#define MB2_SOLVER_LPW 8
+#endif
+constexpr int kSolverLanes = MB2_SOLVER_LPW;
+
+template <int LPW, typename Fn>
+__device__ __forceinline__ void sweepContactLevels(const Contact *contacts, const i32 n, const i32 levels,
+                                                   const int lane, Fn &&solve)
+{
+    constexpr int kPerLane = 32 / LPW;
+    constexpr unsigned kGroupMask = LPW == 32 ? 0xffffffffu : ((1u << (LPW & 31)) - 1u);
+    const int sub = lane & (LPW - 1);
+    const int group_shift = (lane / LPW) * LPW;
+
+    i32 n_max = n, levels_max = levels;
+#pragma unroll
+    for (int o = LPW; o < 32; o <<= 1) {
+        n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+        levels_max = max(levels_max, __shfl_xor_sync(0xffffffffu, levels_max, o));
+    }
+
+    for (i32 base = 0; base < n_max; base += 32) {
+        i32 lv[kPerLane];
+#pragma unroll
+        for (int r = 0; r < kPerLane; r++) {
+            const i32 i = base + r * LPW + sub;
+            lv[r] = i < n ? contacts[i].level : 0;
+        }
+        for (i32 lvl = 1; lvl <= levels_max; lvl++) {
+            unsigned members = 0;
+#pragma unroll
+            for (int r = 0; r < kPerLane; r++) {
+                const unsigned b = __ballot_sync(0xffffffffu, lv[r] == lvl);
+                members |= ((b >> group_shift) & kGroupMask) << (r * LPW);
+            }
+            const int count = __popc(members);
+            for (int k = sub; k < count; k += LPW) {
+                solve(base + (i32)__fns(members, 0, k + 1));
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Joints follow the contacts, sequentially.
+__device__ void phaseSolvePositions(EngineState &S, const PhysicsState &P, const i32 w, const bool valid,
+                                    const int lane)
 {
     const PObjectManager &objs = worldObjects(S, P, w);
 
     Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
-    const i32 n = P.contactCounts[w];
-    const i32 levels = P.contactMaxLevel[w];
-    for (i32 lvl = 1; lvl <= levels; lvl++) {
-        for (i32 base = 0; base < n; base += 32) {
-            const i32 i = base + lane;
-            if (i < n && contacts[i].level == lvl) solveContactPosition(S, P, objs, contacts[i]);
-        }
-        __syncwarp();
-    }
+    const i32 n = valid ? P.contactCounts[w] : 0;
+    const i32 levels = valid ? P.contactMaxLevel[w] : 0;
+    sweepContactLevels<kSolverLanes>(contacts, n, levels, lane, [&](i32 i) {
+        solveContactPosition(S, P, objs, contacts[i]);
+    });
 
     const TableDesc &jt = S.tables[P.jointArchetype];
-    if (lane == 0 && jt.numRows > 0) {
+    if (valid && (lane & (kSolverLanes - 1)) == 0 && jt.numRows > 0) {
         const PJoint *joints = (const PJoint *)jt.columns[P.jointCol];
         const i32 *jw = (const i32 *)jt.columns[1];
         const i32 first = jt.worldOffsets[w];
@@ -2025,22 +2074,17 @@ __device__ void solveContactVelocity(EngineState &S, const PhysicsState &P, cons
     vel2_ref = PVelocity { v2, o2 };
 }
 
-__device__ void phaseSolveVelocities(EngineState &S, const PhysicsState &P, const i32 w, const int lane)
+__device__ void phaseSolveVelocities(EngineState &S, const PhysicsState &P, const i32 w, const bool valid,
+                                     const int lane)
 {
     const PObjectManager &objs = worldObjects(S, P, w);
     const PhysicsWorldParams &params = worldParams(S, P, w);
     const Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
-    const i32 n = P.contactCounts[w];
-    const i32 levels = P.contactMaxLevel[w];
-    for (i32 lvl = 1; lvl <= levels; lvl++) {
-        for (i32 base = 0; base < n; base += 32) {
-            const i32 i = base + lane;
-            if (i < n && contacts[i].level == lvl) {
-                solveContactVelocity(S, P, objs, contacts[i], params.h, params.restitutionThreshold);
-            }
-        }
-        __syncwarp();
-    }
+    const i32 n = valid ? P.contactCounts[w] : 0;
+    const i32 levels = valid ? P.contactMaxLevel[w] : 0;
+    sweepContactLevels<kSolverLanes>(contacts, n, levels, lane, [&](i32 i) {
+        solveContactVelocity(S, P, objs, contacts[i], params.h, params.restitutionThreshold);
+    });
 }
 
 // =============================================================================================
@@ -2128,18 +2172,25 @@ physWorldKernel(EngineState *Sp)
     const PhysicsState &P = *S.physics;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (w >= (i32)S.numWorlds) return;
-    if constexpr (OP == PhaseFindCandidates) {
-        __shared__ CandidateScratch cand_scratch;
-        phaseFindCandidates(S, P, w, lane, warp, cand_scratch);
-    } else if constexpr (OP == PhaseNarrowphase) {
-        __shared__ LevelScratch scratch;
-        phaseNarrowphase(S, P, w, lane, warp, scratch);
-    } else if constexpr (OP == PhaseSolvePositions) {
-        phaseSolvePositions(S, P, w, lane);
-    } else if constexpr (OP == PhaseSolveVelocities) {
-        phaseSolveVelocities(S, P, w, lane);
+    if constexpr (OP == PhaseSolvePositions || OP == PhaseSolveVelocities) {
+        // kSolverLanes lanes per world; the lanes of a warp past the last world idle along
+        const i32 first_w = (i32)((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / kSolverLanes);
+        if (first_w >= (i32)S.numWorlds) return;
+        const i32 my_w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) / kSolverLanes);
+        const bool valid = my_w < (i32)S.numWorlds;
+        const i32 w = valid ? my_w : (i32)S.numWorlds - 1;
+        if constexpr (OP == PhaseSolvePositions) phaseSolvePositions(S, P, w, valid, lane);
+        else phaseSolveVelocities(S, P, w, valid, lane);
+    } else {
+        const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+        if (w >= (i32)S.numWorlds) return;
+        if constexpr (OP == PhaseFindCandidates) {
+            __shared__ CandidateScratch cand_scratch;
+            phaseFindCandidates(S, P, w, lane, warp, cand_scratch);
+        } else if constexpr (OP == PhaseNarrowphase) {
+            __shared__ LevelScratch scratch;
+            phaseNarrowphase(S, P, w, lane, warp, scratch);
+        }
     }
 }
 
@@ -2251,6 +2302,8 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
     const unsigned W = ex->hState->numWorlds;
     const unsigned wgrid = (W + kPhysWarps - 1) / kPhysWarps;
     const unsigned wblock = 32 * kPhysWarps;
+    const unsigned worlds_per_block = wblock / kSolverLanes;
+    const unsigned sgrid = (W + worlds_per_block - 1) / worlds_per_block;
     const dim3 bgrid = bodyGrid(ex);
     for (uint32_t i = 0; i < count; i++) {
         const NodeRecord &rec = recs[i];
@@ -2275,13 +2328,13 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
             physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d);
             break;
         case NodePhysSolvePositions:
-            physWorldKernel<PhaseSolvePositions><<<wgrid, wblock, 0, s>>>(d);
+            physWorldKernel<PhaseSolvePositions><<<sgrid, wblock, 0, s>>>(d);
             break;
         case NodePhysSetVelocities:
             physBodyKernel<PhaseSetVelocities><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysSolveVelocities:
-            physWorldKernel<PhaseSolveVelocities><<<wgrid, wblock, 0, s>>>(d);
+            physWorldKernel<PhaseSolveVelocities><<<sgrid, wblock, 0, s>>>(d);
             break;
         default:
             *err = "unknown physics node kind " + std::to_string(rec.kind);
