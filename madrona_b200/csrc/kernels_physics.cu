@@ -1900,8 +1900,8 @@ __device__ void solveJoint(EngineState &S, const PhysicsState &P, const PObjectM
 // levels inside a chunk run in order, so any two contacts sharing a mutable body
 // keep their sequential order.  Inside a level the members are compacted onto
 // the group's first lanes (ballot + find-nth-set).
-// The solves are latency bound with ~4 contacts per level, so two worlds per
-// warp multiplies the worlds in flight per SM at no register cost (measured on B200, room
+// The solves are latency bound with ~4 contacts per level, so several worlds per
+// warp multiply the worlds in flight per SM at no register cost (measured on B200, room
 // 8192 worlds: 32 lanes/world 1.103 ms/step, 16: 1.097, 8: 1.080).
 #ifndef MB2_SOLVER_LPW
 #define MB2_SOLVER_LPW 8

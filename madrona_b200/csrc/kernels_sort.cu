@@ -150,6 +150,9 @@ sortOnesweepKernel(SortParams p, int pass)
     __shared__ uint32_t warp_hist[kSortWarps][256];
     __shared__ uint32_t digit_base[256];
     __shared__ uint32_t scan_tmp[kSortWarps];
+    __shared__ uint32_t tile_digit_start[256];
+    __shared__ uint32_t stage_keys[kTileItems];
+    __shared__ int32_t stage_idx[kTileItems];
     __shared__ int32_t tile_s;
 
     const int lane = threadIdx.x & 31;
@@ -241,17 +244,43 @@ sortOnesweepKernel(SortParams p, int pass)
             }
             lb[(size_t)tile * 256 + d] = kFlagInclusive | (excl + tile_count);
         }
-        digit_base[d] = bin_excl + excl;
+        // -- the tile's own digit offsets (exclusive scan of tile_count over the 256 digits)
+        {
+            uint32_t incl = tile_count;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) scan_tmp[warp] = incl;
+            __syncthreads();
+            uint32_t warp_off = 0;
+            for (int w = 0; w < warp; w++) warp_off += scan_tmp[w];
+            const uint32_t tile_excl = warp_off + incl - tile_count;
+            tile_digit_start[d] = tile_excl;
+            // global position of the tile's FIRST element of digit d, minus its slot in the tile
+            digit_base[d] = bin_excl + excl - tile_excl;
+        }
         __syncthreads();
 
-        // -- scatter
+        // -- stage the tile in digit order in shared memory ...
 #pragma unroll
         for (int r = 0; r < kItemsPerThread; r++) {
             if (rank[r] == 0xFFFFFFFFu) continue;
             const uint32_t digit = (key[r] >> shift) & 0xffu;
-            const uint32_t pos = digit_base[digit] + warp_hist[warp][digit] + rank[r];
-            keys_out[pos] = key[r];
-            idx_out[pos] = idx[r];
+            const uint32_t slot = tile_digit_start[digit] + warp_hist[warp][digit] + rank[r];
+            stage_keys[slot] = key[r];
+            stage_idx[slot] = idx[r];
+        }
+        __syncthreads();
+
+        // -- ... and write it out slot by slot: runs of equal digits land on
+        //    consecutive addresses, so the scatter is coalesced per run
+        const int32_t tile_items = min(kTileItems, n - tile * kTileItems);
+        for (int32_t slot = threadIdx.x; slot < tile_items; slot += kSortThreads) {
+            const uint32_t k = stage_keys[slot];
+            const uint32_t pos = digit_base[(k >> shift) & 0xffu] + (uint32_t)slot;
+            keys_out[pos] = k;
+            idx_out[pos] = stage_idx[slot];
         }
         __syncthreads();
     }
