@@ -22,6 +22,7 @@
 // they (only) get one extra copy-back launch.
 #include "engine.hpp"
 #include <cstdio>
+#include <cstdlib>
 
 namespace mb2 {
 
@@ -587,7 +588,13 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
 
     const int tiles = (t.capacity + kTileItems - 1) / kTileItems;
     const int hist_grid = std::max(1, std::min(tiles, ex->numSMs * 4));
-    const int sweep_grid = std::max(1, std::min(tiles, ex->numSMs * 2));
+    // ticketed tiles: any grid size is deadlock free; more resident blocks hide the
+    // ranking / look-back latency of each tile
+    static const int sweep_per_sm = [] {
+        const char *v = getenv("MADRONA_B200_SWEEP_BLOCKS_PER_SM");
+        return (v && *v) ? std::max(1, atoi(v)) : 4;   // B200, 3.1M rows: 2 -> 0.659, 3 -> 0.615, 4 -> 0.598, 6 -> 0.599 ms
+    }();
+    const int sweep_grid = std::max(1, std::min(tiles, ex->numSMs * sweep_per_sm));
     sortHistogramKernel<<<hist_grid, kSortThreads, 0, s>>>(p);
     for (int pass = 0; pass < p.numPasses; pass++) {
         sortOnesweepKernel<<<sweep_grid, kSortThreads, 0, s>>>(p, pass);
