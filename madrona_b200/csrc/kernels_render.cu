@@ -216,6 +216,68 @@ __device__ __forceinline__ bool rayTriangle(Vector3 a, Vector3 b, Vector3 c, con
     return true;
 }
 
+// The same test on triangles that were already translated by the (per view, per
+// instance) ray origin and staged in shared memory, with the axis permutation
+// resolved at compile time: rays of a warp mostly share their dominant axis,
+// and the run-time component selects were the single largest cost of the
+// generic version (ncu, profiles/r01_ncu_raycast.csv).  Same operations on the
+// same operands as rayTriangle -> same bits.
+template <int KZ, bool FLIP>
+__device__ __forceinline__ void stagedTriangles(const float *tris, const u32 num_tris, const float Sx,
+                                                const float Sy, const float Sz, float &t_obj, bool &hit,
+                                                Vector3 &n_obj)
+{
+    constexpr int K1 = (KZ + 1) % 3, K2 = (KZ + 2) % 3;
+    constexpr int KX = FLIP ? K2 : K1, KY = FLIP ? K1 : K2;
+    for (u32 tri = 0; tri < num_tris; tri++) {
+        const float *t9 = tris + tri * 9;
+        const float a_kz = t9[KZ], a_kx = t9[KX], a_ky = t9[KY];
+        const float b_kz = t9[3 + KZ], b_kx = t9[3 + KX], b_ky = t9[3 + KY];
+        const float c_kz = t9[6 + KZ], c_kx = t9[6 + KX], c_ky = t9[6 + KY];
+
+        const float Ax = fmaf(-Sx, a_kz, a_kx), Ay = fmaf(-Sy, a_kz, a_ky);
+        const float Bx = fmaf(-Sx, b_kz, b_kx), By = fmaf(-Sy, b_kz, b_ky);
+        const float Cx = fmaf(-Sx, c_kz, c_kx), Cy = fmaf(-Sy, c_kz, c_ky);
+
+        float U = fmaf(Cx, By, -Cy * Bx);
+        float V = fmaf(Ax, Cy, -Ay * Cx);
+        float W = fmaf(Bx, Ay, -By * Ax);
+
+        constexpr float eps = 1e-7;
+        if (U > -eps && U < eps) U = 0.f;
+        if (V > -eps && V < eps) V = 0.f;
+        if (W > -eps && W < eps) W = 0.f;
+
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
+
+        if (U == 0.0f || V == 0.0f || W == 0.0f) {
+            U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+            V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+            W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+            if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
+        }
+
+        const float det = U + V + W;
+        if (det == 0.f) continue;
+
+        const float Az = Sz * a_kz, Bz = Sz * b_kz, Cz = Sz * c_kz;
+        const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
+
+        const u32 sign = __float_as_uint(det) & 0x80000000u;
+        const float xor_T = __uint_as_float(__float_as_uint(T) ^ sign);
+        const float abs_det = copysignf(det, 1.f);
+        if (xor_T < 0.0f || xor_T > t_obj * abs_det) continue;
+
+        const float rcp = 1.0f / det;
+        t_obj = T * rcp;
+        hit = true;
+        const Vector3 A { t9[0], t9[1], t9[2] }, B { t9[3], t9[4], t9[5] }, C { t9[6], t9[7], t9[8] };
+        n_obj = madrona::math::normalize(cross(B - A, C - A));
+    }
+}
+
+constexpr int kTriArena = 640;      // origin-relative triangles staged per block (23 KB)
+
 __global__ void __launch_bounds__(256)
 renderRaycastKernel(EngineState *Sp)
 {
@@ -224,15 +286,22 @@ renderRaycastKernel(EngineState *Sp)
     const TableDesc &out_tbl = S.tables[R.outputArchetype];
     const i32 num_views = min(out_tbl.numRows, R.maxViews);
     const u32 res = R.resolution;
-    const u32 pixel = blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 px = pixel % res, py = pixel / res;
-    const bool in_image = pixel < res * res;
+    // One block traces a whole view (the per-view staging below is paid once);
+    // a warp traces 8 x 4 pixel tiles: coherent rays (same instances entered,
+    // same dominant axis) instead of 32-pixel row segments.
+    const u32 tiles_x = (res + 7) / 8;
+    const u32 num_tiles = tiles_x * ((res + 3) / 4);
     const size_t bytes_per_view = (size_t)res * res * 4;
 
     __shared__ RenderInstance staged[kStagedInstances];
     __shared__ RenderInstance stage_tmp[kStagedInstances];
     __shared__ float stage_key[kStagedInstances];
     __shared__ int stage_count[2];
+    __shared__ float inst_origin[kStagedInstances][3];   // ray origin in the instance's object space
+    __shared__ int inst_tris[kStagedInstances];          // arena offset, -1: not staged, -2: skip instance
+    __shared__ int inst_nt[kStagedInstances];            // triangles of the instance's mesh
+    __shared__ int arena_used;
+    __shared__ float tri_arena[kTriArena * 9];
 
     for (i32 v = blockIdx.y; v < num_views; v += gridDim.y) {
         const RenderView view = R.views[v];
@@ -304,6 +373,60 @@ renderRaycastKernel(EngineState *Sp)
         }
         __syncthreads();
         const i32 num_inst = stage_count[0] + stage_count[1];
+
+        // Per (view, instance) work, hoisted out of the per-ray loop: the ray
+        // origin in object space and the mesh's triangles relative to it.
+        if (threadIdx.x < 64 && threadIdx.x < num_inst) {
+            const int k = threadIdx.x;
+            const RenderInstance &inst = staged[k];
+            int slot = -1;
+            if (inst.scale.x == 0.f || inst.scale.y == 0.f || inst.scale.z == 0.f ||
+                    inst.objectID < 0 || (u32)inst.objectID >= R.numMeshes) {
+                slot = -2;
+            } else {
+                const Quat q { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
+                const Diag3x3 inv_scale = Diag3x3 { inst.scale.x, inst.scale.y, inst.scale.z }.inv();
+                const Vector3 p { inst.position.x, inst.position.y, inst.position.z };
+                const Vector3 o = inv_scale * q.inv().rotateVec(ray_start - p);
+                inst_origin[k][0] = o.x; inst_origin[k][1] = o.y; inst_origin[k][2] = o.z;
+            }
+            inst_tris[k] = slot;
+            inst_nt[k] = slot == -2 ? 0 : (int)R.meshes[inst.objectID].numTriangles;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int used = 0;
+            for (int k = 0; k < num_inst; k++) {
+                if (inst_tris[k] == -2) continue;
+                if (used + inst_nt[k] <= kTriArena) {
+                    inst_tris[k] = used;
+                    used += inst_nt[k];
+                }
+            }
+            arena_used = used;
+        }
+        __syncthreads();
+        // all staged triangle corners in one flat pass (arena slot -> owning instance by scan)
+        for (int e = threadIdx.x; e < arena_used * 3; e += blockDim.x) {
+            const int tri_slot = e / 3;
+            int k = 0;
+            for (int j = 0; j < num_inst; j++) {
+                if (inst_tris[j] >= 0 && inst_tris[j] <= tri_slot) k = j;
+            }
+            const MeshDesc &mesh = R.meshes[staged[k].objectID];
+            const u32 i = (u32)(e - inst_tris[k] * 3);
+            const u32 vi = R.indices[(size_t)mesh.firstTriangle * 3 + i];
+            const Vector3 vert { R.vertices[vi * 3], R.vertices[vi * 3 + 1], R.vertices[vi * 3 + 2] };
+            const Vector3 rel = vert - Vector3 { inst_origin[k][0], inst_origin[k][1], inst_origin[k][2] };
+            float *dst = tri_arena + (size_t)e * 3;
+            dst[0] = rel.x; dst[1] = rel.y; dst[2] = rel.z;
+        }
+        __syncthreads();
+
+        for (u32 tile = threadIdx.x >> 5; tile < num_tiles; tile += blockDim.x >> 5) {
+        const u32 px = (tile % tiles_x) * 8 + (threadIdx.x & 7);
+        const u32 py = (tile / tiles_x) * 4 + ((threadIdx.x & 31) >> 3);
+        const bool in_image = px < res && py < res;
         if (!in_image) continue;
 
         // ---- primary ray (bvh_raycast.cpp:58-88)
@@ -325,14 +448,13 @@ renderRaycastKernel(EngineState *Sp)
             AABB box { { inst.aabbMin[0], inst.aabbMin[1], inst.aabbMin[2] },
                        { inst.aabbMax[0], inst.aabbMax[1], inst.aabbMax[2] } };
             if (!box.rayIntersects(ray_start, inv_dir, 0.f, t_max)) continue;
-            if (inst.scale.x == 0.f || inst.scale.y == 0.f || inst.scale.z == 0.f) continue;
-            if (inst.objectID < 0 || (u32)inst.objectID >= R.numMeshes) continue;
+            const int first_tri = inst_tris[k];
+            if (first_tri == -2) continue;
 
             // object-space ray; t is rescaled by |d'| while inside the mesh
             const Quat q { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
             const Diag3x3 inv_scale = Diag3x3 { inst.scale.x, inst.scale.y, inst.scale.z }.inv();
-            const Vector3 p { inst.position.x, inst.position.y, inst.position.z };
-            const Vector3 o = inv_scale * q.inv().rotateVec(ray_start - p);
+            const Vector3 o { inst_origin[k][0], inst_origin[k][1], inst_origin[k][2] };
             Vector3 d = inv_scale * q.inv().rotateVec(ray_dir);
             const float t_scale = d.length();
             float t_obj = t_max * t_scale;
@@ -343,17 +465,30 @@ renderRaycastKernel(EngineState *Sp)
             const MeshDesc &mesh = R.meshes[inst.objectID];
             bool hit_here = false;
             Vector3 n_obj { 0, 0, 0 };
-            for (u32 tri = 0; tri < mesh.numTriangles; tri++) {
-                const u32 *idx = R.indices + (size_t)(mesh.firstTriangle + tri) * 3;
-                const Vector3 a { R.vertices[idx[0] * 3], R.vertices[idx[0] * 3 + 1], R.vertices[idx[0] * 3 + 2] };
-                const Vector3 b { R.vertices[idx[1] * 3], R.vertices[idx[1] * 3 + 1], R.vertices[idx[1] * 3 + 2] };
-                const Vector3 c { R.vertices[idx[2] * 3], R.vertices[idx[2] * 3 + 1], R.vertices[idx[2] * 3 + 2] };
-                float t;
-                Vector3 n;
-                if (rayTriangle(a, b, c, rs, o, t_obj, &t, &n)) {
-                    t_obj = t;
-                    hit_here = true;
-                    n_obj = n;
+            if (first_tri >= 0) {
+                const float *tris = tri_arena + (size_t)first_tri * 9;
+                const bool flip = rs.kx != (rs.kz + 1) % 3;
+                switch (rs.kz * 2 + (flip ? 1 : 0)) {
+                case 0: stagedTriangles<0, false>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
+                case 1: stagedTriangles<0, true>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
+                case 2: stagedTriangles<1, false>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
+                case 3: stagedTriangles<1, true>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
+                case 4: stagedTriangles<2, false>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
+                default: stagedTriangles<2, true>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
+                }
+            } else {
+                for (u32 tri = 0; tri < mesh.numTriangles; tri++) {
+                    const u32 *idx = R.indices + (size_t)(mesh.firstTriangle + tri) * 3;
+                    const Vector3 a { R.vertices[idx[0] * 3], R.vertices[idx[0] * 3 + 1], R.vertices[idx[0] * 3 + 2] };
+                    const Vector3 b { R.vertices[idx[1] * 3], R.vertices[idx[1] * 3 + 1], R.vertices[idx[1] * 3 + 2] };
+                    const Vector3 c { R.vertices[idx[2] * 3], R.vertices[idx[2] * 3 + 1], R.vertices[idx[2] * 3 + 2] };
+                    float t;
+                    Vector3 n;
+                    if (rayTriangle(a, b, c, rs, o, t_obj, &t, &n)) {
+                        t_obj = t;
+                        hit_here = true;
+                        n_obj = n;
+                    }
                 }
             }
             t_max = t_obj / t_scale;
@@ -385,6 +520,7 @@ renderRaycastKernel(EngineState *Sp)
             rgb[3] = 255;
         }
         (void)hit_normal;
+        }   // tiles of the view
     }
 }
 
@@ -549,9 +685,8 @@ LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err)
         delete g;
         return nullptr;
     }
-    const unsigned pixel_blocks = (R.resolution * R.resolution + 255) / 256;
-    const unsigned view_blocks = (unsigned)std::max(1, std::min(R.maxViews, 32768));
-    renderRaycastKernel<<<dim3(pixel_blocks, view_blocks), 256, 0, ex->stream>>>(ex->dState);
+    const unsigned view_blocks = (unsigned)std::max(1, std::min(R.maxViews, 65535));
+    renderRaycastKernel<<<dim3(1, view_blocks), 256, 0, ex->stream>>>(ex->dState);
     launchStatusCopy(ex, ex->stream);
     cudaError_t e = cudaStreamEndCapture(ex->stream, &g->graph);
     if (e != cudaSuccess || cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) {
