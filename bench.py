@@ -143,7 +143,10 @@ def run_reference_arm(args, wl):
     W = wl["ref_worlds"]
     if not W:
         return None   # GPU-only microbenchmark: no CPU-backend counterpart
-    steps = getattr(args, "ref_steps", None) or (args.steps + args.warmup)
+    # a bounded sample of the workload that is long enough for the CPU backend's
+    # cold start (thread pool, first BVH build) to be amortised -- with only K+W
+    # simulation steps the reference would be timed mostly cold
+    steps = getattr(args, "ref_steps", None) or max(args.steps + args.warmup, wl.get("ref_steps", 2000))
     if not runner.available(desc.name):
         return None
     t0 = time.time()
