@@ -776,37 +776,9 @@ struct HullInWorld {
     Vector3 center;
 };
 
-// vertex transform = R S, normal transform = R S^-1 (renormalised), plane
-// offset through a transformed point of the plane; centre = vertex mean
-// (narrowphase.cpp:151-223).
-__device__ HullInWorld placeHull(const PHalfEdgeMesh &mesh, Vector3 t, Quat r, Diag3x3 s,
-                                 Vector3 *verts, PPlane *planes)
-{
-    const Mat3x3 rot = Mat3x3::fromQuat(r);
-    const Mat3x3 vert_m = rot * s;
-    const Mat3x3 norm_m = rot * s.inv();
-
-    Vector3 center = Vector3::zero();
-    const u32 nv = mesh.numVertices;
-#pragma unroll 1
-    for (u32 i = 0; i < nv; i++) {
-        Vector3 p = vert_m * mesh.vertices[i] + t;
-        verts[i] = p;
-        center += p;
-    }
-    center /= (float)nv;
-
-    const u32 nf = mesh.numFaces;
-#pragma unroll 1
-    for (u32 i = 0; i < nf; i++) {
-        PPlane local = mesh.facePlanes[i];
-        Vector3 on_plane = vert_m * (local.normal * local.d) + t;
-        Vector3 n = (norm_m * local.normal).normalize();
-        planes[i] = PPlane { n, dot(n, on_plane) };
-    }
-    return HullInWorld { &mesh, verts, planes, nv, nf, center };
-}
-
+// (placement: vertex = R S v + t, normal = normalize(R S^-1 n), plane offset through a
+// transformed point of the plane, centre = vertex mean -- narrowphase.cpp:151-223;
+// done by the lanes of the warp in hullHullCooperative, on the fly for hull-plane)
 __device__ __forceinline__ float planeDistance(const PPlane &pl, Vector3 p)
 {
     return dot(p, pl.normal) - pl.d;
@@ -1109,27 +1081,6 @@ __device__ ManifoldOut faceFaceManifold(const PPlane &ref_plane, i32 ref_face, i
     return reduceManifold(ref_plane.normal, src, depths, kept);
 }
 
-__device__ ManifoldOut facePlaneManifold(const PPlane &plane, i32 inc_face, const HullInWorld &h,
-                                         Vector3 *buf)
-{
-    float depths[kClipCap];
-    int kept = 0;
-    u32 he = h.mesh->faceBaseHalfEdges[inc_face];
-    const u32 start = he;
-    do {
-        const PHalfEdge cur = h.mesh->halfEdges[he];
-        he = cur.next;
-        Vector3 p = h.verts[cur.rootVertex];
-        float d = planeDistance(plane, p);
-        if (d <= 0.0f && kept < kClipCap) {
-            buf[kept] = p - d * plane.normal;
-            depths[kept] = -d;
-            kept++;
-        }
-    } while (he != start);
-    return reduceManifold(plane.normal, buf, depths, kept);
-}
-
 // closest points of two segments, clamped (narrowphase.cpp:1037-1071); only the
 // point on segment 1 is used by the caller
 __device__ Vector3 closestOnFirstSegment(Vector3 p1, Vector3 q1, Vector3 p2, Vector3 q2)
@@ -1300,7 +1251,7 @@ __device__ bool narrowphaseSimple(EngineState &S, const PairSetup &ps, Contact &
             }
         }
 
-        Vector3 clip[kClipCap];                       // facePlaneManifold
+        Vector3 clip[kClipCap];                       // incident-face points at or below the plane
         float depths[kClipCap];
         int kept = 0;
         u32 he = am.faceBaseHalfEdges[inc_face];

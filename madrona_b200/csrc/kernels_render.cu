@@ -278,7 +278,7 @@ __device__ __forceinline__ void stagedTriangles(const float *tris, const u32 num
 
 constexpr int kTriArena = 640;      // origin-relative triangles staged per block (23 KB)
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 renderRaycastKernel(EngineState *Sp)
 {
     EngineState &S = *Sp;
