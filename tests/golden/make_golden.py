@@ -42,3 +42,15 @@ if __name__ == "__main__":
         save_golden(name, inputs, outs, W, steps)
         print(name, {k: (v.shape if not isinstance(v, list) else f"{len(v)} frames")
                      for k, v in outs.items()})
+
+    # digest of the reference GJK probe (oracle/gjk_probe.cpp built against the
+    # reference's src/physics/gjk.hpp + geo.cpp): lets the engine's header be
+    # checked where oracle/_ref/gjk_probe_ref is absent
+    if not only or "gjk_probe" in only:
+        import hashlib
+        import subprocess
+        probe = os.path.join(ROOT, "oracle", "_ref", "gjk_probe_ref")
+        text = subprocess.run([probe], capture_output=True, text=True, check=True).stdout
+        with open(os.path.join(ROOT, "tests", "golden", "gjk_probe.sha256"), "w") as f:
+            f.write(hashlib.sha256(text.encode()).hexdigest() + "\n")
+        print("gjk_probe", len(text.splitlines()), "values")
