@@ -506,6 +506,7 @@ static LaunchGraph *buildGraph(Executor *ex, const uint32_t *ids, uint32_t n, co
     g->owner = ex;
     g->name = name ? name : "";
 
+    physicsBeforeGraphCapture(ex);
     cudaError_t e = cudaStreamBeginCapture(ex->stream, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) {
         setError(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));

@@ -26,6 +26,7 @@
 #include "physics_state.h"
 
 #include <madrona/math.hpp>
+#include <madrona/gjk.hpp>
 
 #include <cfloat>
 #include <algorithm>
@@ -125,6 +126,7 @@ struct PhysicsHost {
     PhysicsState *dPhys = nullptr;
     PhysicsState hPhys;
     bool active = false;
+    bool spheres = false;     // some registered object has a sphere primitive (read before graph capture)
 };
 
 // ---- small device helpers ------------------------------------------------------------
@@ -1193,7 +1195,75 @@ __device__ __forceinline__ PairSetup setupPair(const EngineState &S, const Physi
     return ps;
 }
 
+// sphere (a) - hull (b): GJK closest point of the hull to the sphere centre, SAT
+// over the face planes when the centre is inside (narrowphase.cpp:1326-1402).
+// Out of line and by value: rare in the box-world fixtures, inlining the GJK
+// loop doubles the narrowphase kernel's code size, and handing it the caller's
+// PairSetup / Contact by reference would push those into local memory for every
+// pair type (measured: +5 % on the room step).
+struct SphereHullResult {
+    Vector3 point;
+    Vector3 normal;
+    float depth;
+    i32 hit;          // 1 contact, 0 none, -1 hull too large for the staging array
+};
+
+__device__ __noinline__ SphereHullResult sphereHullContact(Vector3 a_pos, float radius, Vector3 b_pos,
+                                                           Quat b_rot, Diag3x3 b_scale,
+                                                           const PHalfEdgeMesh *mesh)
+{
+    const PHalfEdgeMesh &bm = *mesh;
+    SphereHullResult res { Vector3::zero(), Vector3::zero(), 0.f, 0 };
+    if (bm.numVertices > (u32)kMaxHullVerts) {
+        res.hit = -1;
+        return res;
+    }
+    // the hull relative to the sphere centre, so the query point is the origin
+    const Vector3 hull_origin = b_pos - a_pos;
+    const Mat3x3 rot = Mat3x3::fromQuat(b_rot);
+    const Mat3x3 vert_m = rot * b_scale;
+    const Mat3x3 norm_m = rot * b_scale.inv();
+    Vector3 verts[kMaxHullVerts];
+#pragma unroll 1
+    for (u32 i = 0; i < bm.numVertices; i++) verts[i] = vert_m * bm.vertices[i] + hull_origin;
+
+    Vector3 to_hull;
+    const float dist2 = madrona::geo::hullVerticesClosestPointToOriginGJK(verts, bm.numVertices, 1e-10f,
+                                                                         &to_hull);
+    if (dist2 > radius * radius) return res;
+
+    if (dist2 == 0.f) {
+        // centre inside the hull: least-penetrated face (SAT over the face planes)
+        float max_sep = -FLT_MAX;
+        Vector3 sep_normal = Vector3::zero();
+#pragma unroll 1
+        for (u32 f = 0; f < bm.numFaces; f++) {
+            const PPlane local = bm.facePlanes[f];
+            const Vector3 on_plane = vert_m * (local.normal * local.d) + hull_origin;
+            const Vector3 n = (norm_m * local.normal).normalize();
+            const float face_dist = -dot(n, on_plane);
+            if (face_dist > max_sep) {
+                max_sep = face_dist;
+                sep_normal = n;
+            }
+        }
+        if (max_sep > 0.f) return res;      // GJK and SAT disagree by rounding
+        res.point = a_pos + sep_normal * radius;
+        res.normal = sep_normal;
+        res.depth = -max_sep;
+    } else {
+        const float to_hull_len = sqrtf(dist2);
+        const Vector3 normal = to_hull / to_hull_len;
+        res.point = a_pos + normal * radius;
+        res.normal = -normal;
+        res.depth = radius - to_hull_len;
+    }
+    res.hit = 1;
+    return res;
+}
+
 // sphere-sphere (1), sphere-plane (5), hull-plane (6): finished by the lane itself
+template <bool SPHERE_HULL>
 __device__ bool narrowphaseSimple(EngineState &S, const PairSetup &ps, Contact &out)
 {
     switch (ps.test) {
@@ -1272,8 +1342,22 @@ __device__ bool narrowphaseSimple(EngineState &S, const PairSetup &ps, Contact &
         writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, m);
         return true;
     }
+    case 3: {
+        if constexpr (SPHERE_HULL) {
+            const SphereHullResult r = sphereHullContact(ps.aPos, ps.aScale.d0 * ps.aPrim->sphereRadius,
+                                                         ps.bPos, ps.bRot, ps.bScale, &ps.bPrim->hull);
+            if (r.hit < 0) atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+            if (r.hit <= 0) return false;
+            writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, singlePoint(r.point, r.normal, r.depth));
+            return true;
+        } else {
+            // a sphere appeared after the launch graph was built without the
+            // sphere-hull path: rebuild the launch graph
+            atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+            return false;
+        }
+    }
     default:
-        // sphere - hull needs the GJK closest-point routine (geo.cpp:38-59): not in this build
         atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
         return false;
     }
@@ -1518,6 +1602,7 @@ struct LevelScratch {
     HullScratch hulls[kPhysWarps];
 };
 
+template <bool SPHERE_HULL>
 __device__ void phaseNarrowphase(EngineState &S, const PhysicsState &P, const i32 w, const int lane,
                                  const int warp, LevelScratch &scratch)
 {
@@ -1542,7 +1627,7 @@ __device__ void phaseNarrowphase(EngineState &S, const PhysicsState &P, const i3
         PairSetup ps;
         ps.test = 0;
         if (i < n) ps = setupPair(S, P, objs, cands[i]);
-        if (ps.test != 0 && ps.test != 2) hit = narrowphaseSimple(S, ps, c);
+        if (ps.test != 0 && ps.test != 2) hit = narrowphaseSimple<SPHERE_HULL>(S, ps, c);
         u32 hull_pairs = __ballot_sync(0xffffffffu, ps.test == 2);
         while (hull_pairs) {
             const int src = __ffs(hull_pairs) - 1;
@@ -2051,6 +2136,7 @@ __device__ void phaseSolveVelocities(EngineState &S, const PhysicsState &P, cons
 enum PhysPhase : u32 {
     PhaseUpdateLeaves = 1, PhaseRebuild, PhaseRefit, PhaseFindCandidates, PhaseIntegrate,
     PhaseNarrowphase, PhaseSolvePositions, PhaseSetVelocities, PhaseSolveVelocities,
+    PhaseNarrowphaseSpheres,      // narrowphase incl. the sphere - hull (GJK) path
 };
 
 template <u32 OP>
@@ -2113,7 +2199,7 @@ __device__ __forceinline__ void forEachWorldBody(const EngineState &S, const Phy
 #ifndef MB2_NARROW_MINB
 #define MB2_NARROW_MINB 8
 #endif
-constexpr int physMinBlocks(u32 op) { return op == 6u /* PhaseNarrowphase */ ? MB2_NARROW_MINB : 8; }
+constexpr int physMinBlocks(u32 op) { return (op == 6u || op == 10u) /* narrowphase */ ? MB2_NARROW_MINB : 8; }
 
 template <u32 OP>
 __global__ void __launch_bounds__(32 * kPhysWarps, physMinBlocks(OP))
@@ -2140,7 +2226,10 @@ physWorldKernel(EngineState *Sp)
             phaseFindCandidates(S, P, w, lane, warp, cand_scratch);
         } else if constexpr (OP == PhaseNarrowphase) {
             __shared__ LevelScratch scratch;
-            phaseNarrowphase(S, P, w, lane, warp, scratch);
+            phaseNarrowphase<false>(S, P, w, lane, warp, scratch);
+        } else if constexpr (OP == PhaseNarrowphaseSpheres) {
+            __shared__ LevelScratch scratch;
+            phaseNarrowphase<true>(S, P, w, lane, warp, scratch);
         }
     }
 }
@@ -2224,6 +2313,15 @@ bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *, std::stri
     return true;
 }
 
+void physicsBeforeGraphCapture(Executor *ex)
+{
+    PhysicsHost *ph = ex->physics;
+    if (!ph || !ph->active) return;
+    u32 flag = 0;
+    cudaMemcpy(&flag, &ph->dPhys->hasSpherePrims, sizeof(u32), cudaMemcpyDeviceToHost);
+    ph->spheres = flag != 0;
+}
+
 void physicsHostDestroy(Executor *ex)
 {
     delete ex->physics;
@@ -2276,7 +2374,8 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
             physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysNarrowphase:
-            physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d);
+            if (ph->spheres) physWorldKernel<PhaseNarrowphaseSpheres><<<wgrid, wblock, 0, s>>>(d);
+            else physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d);
             break;
         case NodePhysSolvePositions:
             physWorldKernel<PhaseSolvePositions><<<sgrid, wblock, 0, s>>>(d);

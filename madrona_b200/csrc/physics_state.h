@@ -123,6 +123,10 @@ struct PhysicsState {
     u32 paramsArchetype;
     u32 objectDataArchetype;
     u32 jointArchetype;
+    // set by PhysicsSystem::registerEntity when an object with a sphere primitive
+    // joins a world: selects the narrowphase kernel that carries the sphere-hull
+    // (GJK) path
+    u32 hasSpherePrims;
 
     // ---- filled by the host after registerTypes
     u32 numBodyArchetypes;

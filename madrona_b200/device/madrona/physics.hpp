@@ -342,7 +342,21 @@ inline void reset(Context &ctx)
 
 inline broadphase::LeafID registerEntity(Context &ctx, Entity e, base::ObjectID obj_id)
 {
-    return ctx.singleton<broadphase::BVH>().reserveLeaf(e, obj_id);
+    broadphase::BVH &bvh = ctx.singleton<broadphase::BVH>();
+    // tell the executor when spheres are in play (it then launches the narrowphase
+    // variant that carries the sphere - hull path)
+    {
+        const ObjectManager *obj_mgr = (const ObjectManager *)bvh.storage().objMgr;
+        const uint32_t first = obj_mgr->rigidBodyPrimitiveOffsets[obj_id.idx];
+        const uint32_t count = obj_mgr->rigidBodyPrimitiveCounts[obj_id.idx];
+        for (uint32_t i = 0; i < count; i++) {
+            if (obj_mgr->collisionPrimitives[first + i].type == CollisionPrimitive::Type::Sphere) {
+                mb2::PhysicsState *P = mwGPU::engine().physics;
+                if (!P->hasSpherePrims) atomicOr(&P->hasSpherePrims, 1u);
+            }
+        }
+    }
+    return bvh.reserveLeaf(e, obj_id);
 }
 
 inline Entity makeFixedJoint(Context &ctx, Entity e1, Entity e2,

@@ -72,6 +72,11 @@ def _room_objects():
     return room_objects()
 
 
+def _balls_objects():
+    from .objects import balls_objects
+    return balls_objects()
+
+
 def _room_render_cfg(cfg):
     from .render_assets import make_render_config
     return make_render_config(int(cfg.get("resolution", 64)), bool(cfg.get("rgbd", False)))
@@ -134,6 +139,21 @@ SIMS: Dict[str, SimDesc] = {
         objects=_room_objects,
         compile_flags=["-DROOM_ENABLE_RENDER=1"],
         render=_room_render_cfg,
+    ),
+    # spheres: sphere-sphere / sphere-plane / sphere-hull (GJK) contacts, physics only
+    "balls": SimDesc(
+        name="balls",
+        sources=[os.path.join(_ROOT, "balls", "sim.cpp")],
+        num_exports=4,
+        num_taskgraphs=1,
+        inputs=[],
+        outputs=[Slot(0, "body_pos", "float32", (16, 3)), Slot(1, "body_rot", "float32", (16, 4)),
+                 Slot(2, "body_vel", "float32", (16, 6)), Slot(3, "body_entity", "int32", (16, 2))],
+        pack_config=lambda cfg: struct.pack("<Q", int(cfg.get("obj_mgr_ptr", 0))),
+        pack_init=lambda w, cfg: struct.pack("<I", int(cfg.get("seed", 0)) + w),
+        oracle_extra=lambda cfg: [int(cfg.get("seed", 0))],
+        defaults={"seed": 0},
+        objects=_balls_objects,
     ),
     "gridworld": SimDesc(
         name="gridworld",

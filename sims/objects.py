@@ -99,8 +99,9 @@ def _metadata(inv_mass, inv_inertia, mu_s, mu_d) -> bytes:
     return struct.pack("<f3f3f4f2f", inv_mass, *inv_inertia, 0, 0, 0, 1, 0, 0, 0, mu_s, mu_d)
 
 
-def room_objects() -> Tuple[bytes, List[int]]:
-    """Objects of sims/room: 0 Cube, 1 Wall, 2 Agent, 3 Plane (one primitive each)."""
+def room_objects(with_ball: bool = False) -> Tuple[bytes, List[int]]:
+    """Objects of sims/room: 0 Cube, 1 Wall, 2 Agent, 3 Plane (one primitive each);
+    with_ball appends 4 Ball (a sphere of radius 0.5) for sims/balls."""
     mesh = box_half_edge_mesh()
     b = BlobBuilder()
     mgr_off = b.add(b"\0" * 48)
@@ -110,10 +111,11 @@ def room_objects() -> Tuple[bytes, List[int]]:
     pl_off = b.add(mesh["planes"].tobytes())
     vt_off = b.add(mesh["vertices"].tobytes())
 
-    n_obj = 4
+    n_obj = 5 if with_ball else 4
     prim_size = 56
     prims_off = b.add(b"\0" * (prim_size * n_obj), align=16)
-    for i, ty in enumerate([TYPE_HULL, TYPE_HULL, TYPE_HULL, TYPE_PLANE]):
+    prim_types = [TYPE_HULL, TYPE_HULL, TYPE_HULL, TYPE_PLANE] + ([TYPE_SPHERE] if with_ball else [])
+    for i, ty in enumerate(prim_types):
         base = prims_off + i * prim_size
         struct.pack_into("<I", b.buf, base, ty)
         if ty == TYPE_HULL:
@@ -123,11 +125,13 @@ def room_objects() -> Tuple[bytes, List[int]]:
             b.pointer_at(base + 32, vt_off)
             struct.pack_into("<III", b.buf, base + 40, len(mesh["half_edges"]),
                              len(mesh["planes"]), len(mesh["vertices"]))
+        elif ty == TYPE_SPHERE:
+            struct.pack_into("<f", b.buf, base + 8, 0.5)      # CollisionPrimitive::sphere.radius
 
     hull_aabb = struct.pack("<6f", -0.5, -0.5, -0.5, 0.5, 0.5, 0.5)
     big = 1.0e5
     plane_aabb = struct.pack("<6f", -big, -big, -big, big, big, 0.0)
-    aabbs = hull_aabb * 3 + plane_aabb
+    aabbs = hull_aabb * 3 + plane_aabb + (hull_aabb if with_ball else b"")
     prim_aabb_off = b.add(aabbs)
     body_aabb_off = b.add(aabbs)
     offs_off = b.add(np.arange(n_obj, dtype=np.uint32).tobytes())
@@ -146,11 +150,20 @@ def room_objects() -> Tuple[bytes, List[int]]:
     agent_inv_i = box_inv_inertia(agent_m, 1.0, 1.0, 1.5)
     meta += _metadata(np.float32(1.0 / agent_m), [0.0, 0.0, agent_inv_i[2]], 0.5, 0.5)  # yaw only
     meta += _metadata(0.0, [0.0, 0.0, 0.0], 0.5, 0.5)                      # plane
+    if with_ball:
+        # solid sphere used at scale 1.2 (radius 0.6): I = 2/5 m r^2
+        ball_m, ball_r = 5.0, 0.6
+        inv_i = np.float32(1.0 / (0.4 * ball_m * ball_r * ball_r))
+        meta += _metadata(np.float32(1.0 / ball_m), [inv_i, inv_i, inv_i], 0.5, 0.5)
     meta_off = b.add(meta)
 
     for i, target in enumerate([prims_off, prim_aabb_off, body_aabb_off, offs_off, cnts_off, meta_off]):
         b.pointer_at(mgr_off + 8 * i, target)
     return bytes(b.buf), b.relocs
+
+
+def balls_objects() -> Tuple[bytes, List[int]]:
+    return room_objects(with_ball=True)
 
 
 def relocate(blob: bytes, relocs: Sequence[int], base_address: int) -> bytes:

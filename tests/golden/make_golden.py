@@ -30,6 +30,8 @@ CASES = [
     ("room_w4_s210", "room", 4, 210, {"episode_len": 100, "seed": 21}),
     # same fixture with agent 0 grabbing / releasing cubes through fixed joints
     ("room_grab_w3_s120", "room", 3, 120, {"episode_len": 70, "seed": 5, "grab_period": 5}),
+    # spheres: sphere-sphere, sphere-plane and sphere-hull (GJK) contacts
+    ("balls_w6_s160", "balls", 6, 160, {"seed": 3}),
 ]
 
 if __name__ == "__main__":
