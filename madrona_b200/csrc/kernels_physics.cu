@@ -546,7 +546,8 @@ __device__ __forceinline__ void forEachPartner(const WorldBVH &bvh, const PairVi
     }
 }
 
-constexpr int kMaxStagedLeaves = 64;
+constexpr int kMaxStagedLeaves = 128;          // bodies per world the candidate search handles
+constexpr int kLeafMaskWords = kMaxStagedLeaves / 64;
 
 struct StagedLeaf {
     float box[6];       // the leaf's slot in its parent node (grow-only since the last rebuild)
@@ -578,7 +579,6 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
 
     const i32 num_leaves = bvh.numTraversal;
     if (num_leaves > kMaxStagedLeaves) {
-        // TODO(next round): window the staged list; sized for <= 64 bodies/world today
         if (lane == 0) atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
         return;
     }
@@ -631,17 +631,23 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
                 box = AABB { { lb.pMin.x, lb.pMin.y, lb.pMin.z }, { lb.pMax.x, lb.pMax.y, lb.pMax.z } };
             }
 
-            // stage 2: which staged leaves does this body pair with (bit k)
-            unsigned long long partners = 0;
+            // stage 2: which staged leaves does this body pair with (bit k of word k / 64)
+            unsigned long long partners[kLeafMaskWords];
+#pragma unroll
+            for (int wd = 0; wd < kLeafMaskWords; wd++) partners[wd] = 0;
             i32 mine = 0;
-            for (i32 k = 0; k < num_leaves; k++) {
-                const StagedLeaf &sl = staged[k];
-                const AABB other { { sl.box[0], sl.box[1], sl.box[2] }, { sl.box[3], sl.box[4], sl.box[5] } };
-                const bool pair = valid && sl.prims != 0 && box.overlaps(other) &&
-                    self_id < sl.entityID && !(self_static && sl.isStatic);
-                if (pair) {
-                    partners |= 1ull << k;
-                    mine += (i32)(self_prims * sl.prims);
+#pragma unroll
+            for (int wd = 0; wd < kLeafMaskWords; wd++) {
+                const i32 k_end = min(num_leaves, (wd + 1) * 64);
+                for (i32 k = wd * 64; k < k_end; k++) {
+                    const StagedLeaf &sl = staged[k];
+                    const AABB other { { sl.box[0], sl.box[1], sl.box[2] }, { sl.box[3], sl.box[4], sl.box[5] } };
+                    const bool pair = valid && sl.prims != 0 && box.overlaps(other) &&
+                        self_id < sl.entityID && !(self_static && sl.isStatic);
+                    if (pair) {
+                        partners[wd] |= 1ull << (k - wd * 64);
+                        mine += (i32)(self_prims * sl.prims);
+                    }
                 }
             }
             // exclusive scan across the warp = emission offsets in row order
@@ -652,16 +658,20 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
             }
             const i32 total = __shfl_sync(0xffffffffu, incl, 31);
             i32 at = running + incl - mine;
-            while (partners) {
-                const int k = __ffsll((long long)partners) - 1;
-                partners &= partners - 1;
-                const StagedLeaf &sl = staged[k];
-                const u32 checks = self_prims * sl.prims;
-                for (u32 c = 0; c < checks; c++) {
-                    if (at < P.maxCandidatesPerWorld) {
-                        out[at] = Candidate { b.archetype, row, sl.arch, sl.row, c / sl.prims, c % sl.prims };
+#pragma unroll
+            for (int wd = 0; wd < kLeafMaskWords; wd++) {
+                unsigned long long word = partners[wd];
+                while (word) {
+                    const int k = wd * 64 + __ffsll((long long)word) - 1;
+                    word &= word - 1;
+                    const StagedLeaf &sl = staged[k];
+                    const u32 checks = self_prims * sl.prims;
+                    for (u32 c = 0; c < checks; c++) {
+                        if (at < P.maxCandidatesPerWorld) {
+                            out[at] = Candidate { b.archetype, row, sl.arch, sl.row, c / sl.prims, c % sl.prims };
+                        }
+                        at++;
                     }
-                    at++;
                 }
             }
             running += total;

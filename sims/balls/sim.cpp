@@ -12,7 +12,6 @@ namespace balls {
 
 constexpr float kDeltaT = 0.04f;
 constexpr CountT kNumSubsteps = 4;
-constexpr float kPen = 4.f;            // pen interior: [-4, 4]^2
 constexpr float kWallThick = 0.5f;
 constexpr float kWallHeight = 8.f;     // tall: the volley stays inside the pen
 constexpr float kBallScale = 1.2f;     // radius 0.6
@@ -86,18 +85,20 @@ Sim::Sim(Engine &ctx, const Config &cfg, const WorldInit &init)
              Diag3x3 { kWallThick, 2.f * kPen, kWallHeight }, SimObject::Wall,
              ResponseType::Static, still);
 
-    // loose cubes resting on the floor
+    // loose cubes resting on the floor, spread over the pen
     for (int32_t i = 0; i < kNumCubes; i++) {
-        float x = -2.5f + 2.5f * (float)i + (rng.sampleUniform() - 0.5f);
-        float y = (rng.sampleUniform() - 0.5f) * 4.f;
+        float span = 2.f * (kPen - 1.5f);
+        float x = -0.5f * span + span * ((float)i + 0.5f) / (float)kNumCubes +
+            (rng.sampleUniform() - 0.5f);
+        float y = (rng.sampleUniform() - 0.5f) * kPen;
         makeBody(ctx, Vector3 { x, y, 0.75f }, upright, Diag3x3 { 1.5f, 1.5f, 1.5f },
                  SimObject::Cube, ResponseType::Dynamic, still);
     }
 
-    // balls: dropped from different heights, thrown at the walls and the cubes.
+    // balls: dropped from different heights, thrown at the walls and the cubes
     for (int32_t i = 0; i < kNumBalls; i++) {
-        float x = (rng.sampleUniform() - 0.5f) * 6.f;
-        float y = (rng.sampleUniform() - 0.5f) * 6.f;
+        float x = (rng.sampleUniform() - 0.5f) * 1.5f * kPen;
+        float y = (rng.sampleUniform() - 0.5f) * 1.5f * kPen;
         float z = 0.6f + 0.9f * (float)(i % 4) + rng.sampleUniform();
         Vector3 vel { (rng.sampleUniform() - 0.5f) * 8.f,
                       (rng.sampleUniform() - 0.5f) * 8.f,

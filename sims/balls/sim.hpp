@@ -27,8 +27,17 @@ using madrona::phys::ExternalForce;
 using madrona::phys::ExternalTorque;
 
 constexpr int32_t kNumWalls = 4;
+#ifdef BALLS_MANY
+// build variant: 95 bodies per world (> 64: more than one word of the engine's
+// candidate-search leaf masks), a bigger pen
+constexpr int32_t kNumCubes = 10;
+constexpr int32_t kNumBalls = 80;
+constexpr float kPen = 9.f;            // pen interior: [-kPen, kPen]^2
+#else
 constexpr int32_t kNumCubes = 3;
 constexpr int32_t kNumBalls = 8;
+constexpr float kPen = 4.f;
+#endif
 constexpr int32_t kMaxBodies = 1 + kNumWalls + kNumCubes + kNumBalls;
 
 enum class ExportID : uint32_t {

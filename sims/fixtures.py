@@ -155,6 +155,22 @@ SIMS: Dict[str, SimDesc] = {
         defaults={"seed": 0},
         objects=_balls_objects,
     ),
+    # build variant with 95 bodies per world (more than one 64-bit word of leaf masks)
+    "balls_many": SimDesc(
+        name="balls_many",
+        sources=[os.path.join(_ROOT, "balls", "sim.cpp")],
+        num_exports=4,
+        num_taskgraphs=1,
+        inputs=[],
+        outputs=[Slot(0, "body_pos", "float32", (95, 3)), Slot(1, "body_rot", "float32", (95, 4)),
+                 Slot(2, "body_vel", "float32", (95, 6)), Slot(3, "body_entity", "int32", (95, 2))],
+        pack_config=lambda cfg: struct.pack("<Q", int(cfg.get("obj_mgr_ptr", 0))),
+        pack_init=lambda w, cfg: struct.pack("<I", int(cfg.get("seed", 0)) + w),
+        oracle_extra=lambda cfg: [int(cfg.get("seed", 0))],
+        defaults={"seed": 0},
+        objects=_balls_objects,
+        compile_flags=["-DBALLS_MANY=1"],
+    ),
     "gridworld": SimDesc(
         name="gridworld",
         sources=[os.path.join(_ROOT, "gridworld", "sim.cpp")],

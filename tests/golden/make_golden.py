@@ -32,6 +32,8 @@ CASES = [
     ("room_grab_w3_s120", "room", 3, 120, {"episode_len": 70, "seed": 5, "grab_period": 5}),
     # spheres: sphere-sphere, sphere-plane and sphere-hull (GJK) contacts
     ("balls_w6_s160", "balls", 6, 160, {"seed": 3}),
+    # 95 bodies per world: candidate search beyond one 64-leaf mask word, ~300 contacts per world
+    ("balls_many_w2_s60", "balls_many", 2, 60, {"seed": 9}),
 ]
 
 if __name__ == "__main__":

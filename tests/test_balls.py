@@ -60,3 +60,39 @@ def test_gpu_matches_live_reference_many_worlds():
     ref, _ = runner.run_reference(SIMS["balls"], W, steps, {}, cfg, workers=4)
     got, _ = rollout_gpu("balls", W, steps, {}, cfg)
     assert_traces_equal(got, ref, exact=EXACT, rtol=1e-4, atol=1e-5)
+
+
+# ---- build variant with 95 bodies per world (-DBALLS_MANY=1) ---------------------------------
+MANY_CFG = {"seed": 9}
+# more rows and pairs than the defaults allow for (64 rows, 256 candidates, 128 contacts per world)
+MANY_ENV = {"MADRONA_B200_MAX_CANDIDATES_PER_WORLD": "4096", "MADRONA_B200_MAX_CONTACTS_PER_WORLD": "2048",
+            "MADRONA_B200_ROWS_PER_WORLD": "128"}
+
+
+@pytest.mark.skipif(not runner.available("balls_many"), reason="oracle/_ref not built")
+def test_many_reference_backend_reproduces_golden():
+    W, steps, ins, outs = load_golden("balls_many_w2_s60")
+    got, _ = runner.run_reference(SIMS["balls_many"], W, steps, ins, MANY_CFG, workers=1)
+    assert_traces_equal(got, outs)
+
+
+@pytest.mark.gpu
+def test_many_gpu_matches_golden(monkeypatch):
+    for k, v in MANY_ENV.items():
+        monkeypatch.setenv(k, v)
+    W, steps, ins, outs = load_golden("balls_many_w2_s60")
+    assert outs["body_pos"].shape[2] == 95
+    got, _ = rollout_gpu("balls_many", W, steps, ins, MANY_CFG)
+    assert_traces_equal(got, outs, exact=EXACT, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not runner.available("balls_many"), reason="oracle/_ref not built")
+def test_many_gpu_matches_live_reference(monkeypatch):
+    for k, v in MANY_ENV.items():
+        monkeypatch.setenv(k, v)
+    W, steps = 48, 80
+    cfg = {"seed": 31000}
+    ref, _ = runner.run_reference(SIMS["balls_many"], W, steps, {}, cfg, workers=4)
+    got, _ = rollout_gpu("balls_many", W, steps, {}, cfg)
+    assert_traces_equal(got, ref, exact=EXACT, rtol=1e-4, atol=1e-5)

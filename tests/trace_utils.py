@@ -36,7 +36,7 @@ def make_inputs(sim: str, num_worlds: int, num_steps: int, seed: int = 0) -> Dic
             "reset": (rng.random((num_steps, num_worlds, 1)) < 0.005).astype(np.int32),
             "action": act.astype(np.int32),
         }
-    if sim == "balls":
+    if sim in ("balls", "balls_many"):
         return {}          # physics only: no inputs
     raise KeyError(sim)
 
