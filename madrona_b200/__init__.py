@@ -17,3 +17,4 @@ from .executor import (  # noqa: F401
     library_path,
     precompile,
 )
+from .tensor import Tensor, TensorElementType  # noqa: F401

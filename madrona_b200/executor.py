@@ -329,6 +329,11 @@ class MWCudaExecutor:
         view = _CudaView(self.getExported(slot), shape, _TYPESTR[dtype])
         return torch.as_tensor(view, device=f"cuda:{self.gpu_id}")
 
+    def exportedTensor(self, slot: int, type, dimensions: Sequence[int]):
+        """madrona::py::Tensor over an exported column (what a sim's Manager returns)."""
+        from .tensor import Tensor
+        return Tensor(self.getExported(slot), type, dimensions, gpu_id=self.gpu_id)
+
     def close(self) -> None:
         if self._h:
             self._lib.mb2_executor_destroy(self._h)
