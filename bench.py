@@ -124,6 +124,11 @@ def make_actions(desc, sim, W, steps, seed):
             angle = rng.integers(0, 8, size=(steps, W, 2))
             rot = rng.integers(0, 5, size=(steps, W, 2))
             out[s.name] = np.stack([amount, angle, rot], axis=-1).astype(s.dtype)
+        elif sim == "arena":
+            shape = (steps, W, 6)
+            out[s.name] = np.stack([rng.integers(0, 4, size=shape), rng.integers(0, 8, size=shape),
+                                    rng.integers(0, 5, size=shape),
+                                    (rng.random(shape) < 0.1).astype(np.int64)], axis=-1).astype(s.dtype)
         else:
             out[s.name] = rng.integers(0, 4, size=(steps, W) + s.per_world).astype(s.dtype)
     return out

@@ -22,4 +22,13 @@ EXTRA_WORKLOADS["room_render"] = dict(
     ref_worlds=0, taskgraphs=[0], render=True,
     desc="rigid-body room + 2 cameras/world, 64x64 RGBA8 + f32 depth by the batch ray caster "
          "(BASELINE configs[3] class; GPU only: the reference CPU backend cannot ray cast)")
+# BASELINE.json configs[2]: "Hide&Seek 4096 worlds/GPU, full XPBD rigid-body + BVH, 1->8 B200"
+EXTRA_WORKLOADS["arena"] = dict(
+    sim="arena", worlds=4096, cfg={"episode_len": 200, "seed": 0},
+    ref_worlds=512, ref_steps=1500, taskgraphs=[0],
+    desc="rigid-body arena (Hide&Seek-class fixture, BASELINE configs[2]): 49 bodies/world (6 hexagonal-prism "
+         "agents, 12 cubes, 8 long boxes, 3 wedge ramps, 2 barrels, 2 latched doors, 15 static hulls, plane), "
+         "fixed joints (latches, grab) + one-step hinge joints (shove), BVH broadphase + SAT narrowphase + XPBD "
+         "4 substeps dt=0.04, 16-ray lidar + 5 line-of-sight rays per agent, episode reset every 200 steps "
+         "(27 bodies + joints destroyed and recreated), no render")
 EXTRA_DEFAULT = "room"

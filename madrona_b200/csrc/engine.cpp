@@ -259,8 +259,11 @@ static bool createExecutor(Executor *ex, const mb2_state_config *sc,
                  std::to_string(prop.major) + std::to_string(prop.minor) + ")");
         return false;
     }
-    MB2_CUDA(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
-    ex->rowsPerWorldHint = envU64("MADRONA_B200_ROWS_PER_WORLD", 64);
+    // a blocking stream, like the reference's cu::makeStream() (plain
+    // cudaStreamCreate): work the caller queued on the legacy default stream --
+    // torch's `actions.copy_(...)` -- is ordered before the step graph
+    MB2_CUDA(cudaStreamCreate(&ex->stream));
+    ex->rowsPerWorldHint = envU64("MADRONA_B200_ROWS_PER_WORLD", 128);
 
     // ---- JIT the simulator
     std::vector<std::string> sources, flags;

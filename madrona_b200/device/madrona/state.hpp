@@ -183,8 +183,13 @@ inline int32_t appendRow(mb2::TableDesc &tbl, uint32_t archetype_id)
     int rank = __popc(peers & ((1u << lane) - 1u));
     int32_t base = 0;
     if ((int)lane == leader) {
-        base = atomicAdd(&tbl.numRows, __popc(peers));
+        const int32_t count = __popc(peers);
+        base = atomicAdd(&tbl.numRows, count);
         tbl.needsSort = 1;
+        // overflow: pull the row count back to the capacity so the later nodes
+        // of the same graph (which size their loops and scratch by numRows)
+        // stay inside the allocation; the step still reports the error
+        if (base + count > tbl.capacity) atomicMin(&tbl.numRows, tbl.capacity);
     }
     base = __shfl_sync(peers, base, leader);
     int32_t row = base + rank;

@@ -58,6 +58,40 @@ inline Args parseArgs(int argc, char **argv)
     return a;
 }
 
+// ObjectManager blob written by sims/objects.py:write_blob_file (u64 size,
+// u64 numRelocs, relocs[], blob): loaded and relocated to host addresses.
+inline void *loadObjectsBlob(const char *path)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        fprintf(stderr, "cannot open objects blob %s\n", path);
+        exit(1);
+    }
+    uint64_t size = 0, num_relocs = 0;
+    if (fread(&size, 8, 1, f) != 1 || fread(&num_relocs, 8, 1, f) != 1) exit(1);
+    std::vector<uint64_t> relocs(num_relocs);
+    if (num_relocs && fread(relocs.data(), 8, num_relocs, f) != num_relocs) exit(1);
+    char *blob = (char *)aligned_alloc(64, (size + 63) / 64 * 64);
+    if (fread(blob, 1, size, f) != size) exit(1);
+    fclose(f);
+    for (uint64_t where : relocs) {
+        uint64_t off;
+        memcpy(&off, blob + where, 8);
+        uint64_t addr = (uint64_t)(uintptr_t)blob + off;
+        memcpy(blob + where, &addr, 8);
+    }
+    return blob;
+}
+
+inline const char *objectsPathArg(int argc, char **argv)
+{
+    for (int i = 1; i + 1 < argc; i++) {
+        if (!strcmp(argv[i], "--objects")) return argv[i + 1];
+    }
+    fprintf(stderr, "--objects <blob> required\n");
+    exit(1);
+}
+
 template <typename ExecT>
 int runTrace(ExecT &exec, const Args &args,
              const std::vector<InSlot> &ins, const std::vector<OutSlot> &outs)

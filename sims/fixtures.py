@@ -77,6 +77,11 @@ def _balls_objects():
     return balls_objects()
 
 
+def _arena_objects():
+    from .objects import arena_objects
+    return arena_objects()
+
+
 def _room_render_cfg(cfg):
     from .render_assets import make_render_config
     return make_render_config(int(cfg.get("resolution", 64)), bool(cfg.get("rgbd", False)))
@@ -118,6 +123,30 @@ SIMS: Dict[str, SimDesc] = {
                                   int(cfg.get("grab_period", 0))],
         defaults={"episode_len": 100, "seed": 0, "grab_period": 0},
         objects=_room_objects,
+    ),
+    # Hide&Seek-class arena (BASELINE configs[2]): 49 bodies, 6 agents, wedge / hexagonal hulls,
+    # hinge joints (doors) + fixed joints (grab), entity churn on every episode reset
+    "arena": SimDesc(
+        name="arena",
+        sources=[os.path.join(_ROOT, "arena", "sim.cpp")],
+        num_exports=15,
+        num_taskgraphs=1,
+        inputs=[Slot(0, "reset", "int32", (1,)), Slot(1, "action", "int32", (6, 4))],
+        outputs=[Slot(2, "reward", "float32", (6,)), Slot(3, "done", "int32", (6,)),
+                 Slot(4, "self_obs", "float32", (6, 10)), Slot(5, "other_obs", "float32", (6, 5, 4)),
+                 Slot(6, "lidar", "float32", (6, 16, 2)),
+                 Slot(7, "agent_pos", "float32", (6, 3)), Slot(8, "agent_rot", "float32", (6, 4)),
+                 Slot(9, "body_count", "int32", (1,)), Slot(10, "joint_count", "int32", (1,)),
+                 Slot(11, "body_pos", "float32", (3,), dynamic=True),
+                 Slot(12, "body_rot", "float32", (4,), dynamic=True),
+                 Slot(13, "body_entity", "int32", (2,), dynamic=True),
+                 Slot(14, "body_vel", "float32", (6,), dynamic=True)],
+        pack_config=lambda cfg: struct.pack("<QII", int(cfg.get("obj_mgr_ptr", 0)),
+                                            int(cfg["episode_len"]), 0),
+        pack_init=_room_init,
+        oracle_extra=lambda cfg: [int(cfg["episode_len"]), int(cfg.get("seed", 0))],
+        defaults={"episode_len": 100, "seed": 0},
+        objects=_arena_objects,
     ),
     # the room fixture built with -DROOM_ENABLE_RENDER=1 (BASELINE configs[3]); GPU only:
     # the reference CPU backend cannot ray cast (src/render/ecs_system.cpp:684-689)

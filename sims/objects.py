@@ -180,3 +180,116 @@ def write_blob_file(path: str, blob: bytes, relocs: Sequence[int]) -> None:
         f.write(struct.pack("<QQ", len(blob), len(relocs)))
         f.write(np.asarray(relocs, dtype=np.uint64).tobytes())
         f.write(blob)
+
+
+# ---- generic builder (arbitrary convex hulls) ---------------------------------------------
+
+def orient_faces(verts: np.ndarray, faces: Sequence[Sequence[int]]):
+    """Reverse loops whose normal points at the hull centroid (=> CCW seen from outside)."""
+    centroid = np.asarray(verts, dtype=np.float64).mean(axis=0)
+    out = []
+    for loop in faces:
+        p = np.asarray([verts[i] for i in loop], dtype=np.float64)
+        nrm = np.cross(p[1] - p[0], p[2] - p[0])
+        out.append(list(loop) if np.dot(nrm, p.mean(axis=0) - centroid) > 0 else list(reversed(loop)))
+    return out
+
+
+def wedge_half_edge_mesh():
+    """Unit ramp: right triangle in x-z (legs 1, right angle at the -x/-z corner)
+    extruded along y; coordinates relative to the centroid."""
+    t = 1.0 / 3.0
+    tri = [(-t, -t), (2 * t, -t), (-t, 2 * t)]
+    v = np.array([[x, y, z] for y in (-0.5, 0.5) for (x, z) in tri], dtype=np.float32)
+    faces = [[0, 1, 2], [3, 4, 5], [0, 1, 4, 3], [0, 2, 5, 3], [1, 2, 5, 4]]
+    return build_half_edge_mesh(v, orient_faces(v, faces))
+
+
+def hex_prism_half_edge_mesh():
+    """Unit hexagonal prism: circumradius 0.5, height 1 (12 vertices, 8 faces, 18 edges)."""
+    s = 0.4330127
+    ring = [(0.5, 0.0), (0.25, s), (-0.25, s), (-0.5, 0.0), (-0.25, -s), (0.25, -s)]
+    v = np.array([[x, y, z] for z in (-0.5, 0.5) for (x, y) in ring], dtype=np.float32)
+    faces = [list(range(6)), list(range(6, 12))] + [[i, (i + 1) % 6, (i + 1) % 6 + 6, i + 6] for i in range(6)]
+    return build_half_edge_mesh(v, orient_faces(v, faces))
+
+
+def build_objects(specs) -> Tuple[bytes, List[int]]:
+    """specs: one dict per object -- {"mesh": <half-edge mesh dict> | "plane" | ("sphere", r),
+    "meta": bytes(52)}; one primitive per object.  Same blob layout as room_objects()."""
+    b = BlobBuilder()
+    mgr_off = b.add(b"\0" * 48)
+    mesh_offs = {}
+    for sp in specs:
+        m = sp["mesh"]
+        if isinstance(m, dict) and id(m) not in mesh_offs:
+            mesh_offs[id(m)] = (b.add(m["half_edges"].tobytes()), b.add(m["face_base"].tobytes()),
+                                b.add(m["planes"].tobytes()), b.add(m["vertices"].tobytes()))
+    n_obj = len(specs)
+    prim_size = 56
+    prims_off = b.add(b"\0" * (prim_size * n_obj), align=16)
+    aabbs = b""
+    big = 1.0e5
+    for i, sp in enumerate(specs):
+        base = prims_off + i * prim_size
+        m = sp["mesh"]
+        if isinstance(m, dict):
+            struct.pack_into("<I", b.buf, base, TYPE_HULL)
+            he, fb, pl, vt = mesh_offs[id(m)]
+            b.pointer_at(base + 8, he)
+            b.pointer_at(base + 16, fb)
+            b.pointer_at(base + 24, pl)
+            b.pointer_at(base + 32, vt)
+            struct.pack_into("<III", b.buf, base + 40, len(m["half_edges"]), len(m["planes"]),
+                             len(m["vertices"]))
+            lo, hi = m["vertices"].min(axis=0), m["vertices"].max(axis=0)
+            aabbs += struct.pack("<6f", *lo, *hi)
+        elif m == "plane":
+            struct.pack_into("<I", b.buf, base, TYPE_PLANE)
+            aabbs += struct.pack("<6f", -big, -big, -big, big, big, 0.0)
+        else:
+            struct.pack_into("<I", b.buf, base, TYPE_SPHERE)
+            struct.pack_into("<f", b.buf, base + 8, float(m[1]))
+            aabbs += struct.pack("<6f", *([-m[1]] * 3), *([m[1]] * 3))
+    prim_aabb_off = b.add(aabbs)
+    body_aabb_off = b.add(aabbs)
+    offs_off = b.add(np.arange(n_obj, dtype=np.uint32).tobytes())
+    cnts_off = b.add(np.ones(n_obj, dtype=np.uint32).tobytes())
+    meta_off = b.add(b"".join(sp["meta"] for sp in specs))
+    for i, target in enumerate([prims_off, prim_aabb_off, body_aabb_off, offs_off, cnts_off, meta_off]):
+        b.pointer_at(mgr_off + 8 * i, target)
+    return bytes(b.buf), b.relocs
+
+
+def _box_inv_inertia(mass, sx, sy, sz):
+    ix = mass / 12.0 * (sy * sy + sz * sz)
+    iy = mass / 12.0 * (sx * sx + sz * sz)
+    iz = mass / 12.0 * (sx * sx + sy * sy)
+    return [np.float32(1.0 / ix), np.float32(1.0 / iy), np.float32(1.0 / iz)]
+
+
+def arena_objects() -> Tuple[bytes, List[int]]:
+    """Objects of sims/arena, in SimObject order: Cube, LongBox, Ramp, Barrel, Door, Wall,
+    Pillar, Agent, Plane.  Inertia tensors are those of the bounding box at the scale the
+    fixture uses the object at (the wedge / prism hulls are approximated by their boxes)."""
+    box, wedge, hexp = box_half_edge_mesh(), wedge_half_edge_mesh(), hex_prism_half_edge_mesh()
+    static = _metadata(0.0, [0.0, 0.0, 0.0], 0.5, 0.5)
+
+    def dyn(mass, sx, sy, sz, mu_s=0.5, mu_d=0.5):
+        return _metadata(np.float32(1.0 / mass), _box_inv_inertia(mass, sx, sy, sz), mu_s, mu_d)
+
+    agent_m = 50.0
+    agent_inv_i = _box_inv_inertia(agent_m, 1.0, 1.0, 1.5)
+    specs = [
+        dict(mesh=box, meta=dyn(10.0, 1.5, 1.5, 1.5, 0.5, 0.75)),            # Cube
+        dict(mesh=box, meta=dyn(12.0, 2.4, 0.8, 1.0)),                       # LongBox
+        dict(mesh=wedge, meta=dyn(15.0, 2.1, 2.0, 1.5)),                     # Ramp
+        dict(mesh=hexp, meta=dyn(8.0, 1.2, 1.2, 1.2)),                       # Barrel
+        dict(mesh=box, meta=dyn(20.0, 2.3, 0.3, 2.0)),                       # Door
+        dict(mesh=box, meta=static),                                         # Wall
+        dict(mesh=hexp, meta=static),                                        # Pillar
+        dict(mesh=hexp, meta=_metadata(np.float32(1.0 / agent_m),            # Agent: yaw only
+                                       [0.0, 0.0, agent_inv_i[2]], 0.5, 0.5)),
+        dict(mesh="plane", meta=static),                                     # Plane
+    ]
+    return build_objects(specs)

@@ -30,6 +30,9 @@ CASES = [
     ("room_w4_s210", "room", 4, 210, {"episode_len": 100, "seed": 21}),
     # same fixture with agent 0 grabbing / releasing cubes through fixed joints
     ("room_grab_w3_s120", "room", 3, 120, {"episode_len": 70, "seed": 5, "grab_period": 5}),
+    # Hide&Seek-class arena: wedge / hexagonal hulls, latched doors (fixed joints to static
+    # walls), grab (fixed) and shove (one-step hinge) joints, two resets inside the trace
+    ("arena_w2_s200", "arena", 2, 200, {"episode_len": 90, "seed": 17}),
     # spheres: sphere-sphere, sphere-plane and sphere-hull (GJK) contacts
     ("balls_w6_s160", "balls", 6, 160, {"seed": 3}),
     # 95 bodies per world: candidate search beyond one 64-leaf mask word, ~300 contacts per world

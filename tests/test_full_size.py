@@ -24,7 +24,7 @@ def _rollout_prefix(sim, W, steps, ins, cfg, keep_worlds, rows_per_world=None):
         for s in desc.inputs:
             full = torch.zeros((W,) + s.per_world, dtype=in_t[s.name].dtype, device=in_t[s.name].device)
             full[:keep_worlds] = torch.from_numpy(np.ascontiguousarray(ins[s.name][step])).to(full.device)
-            if s.name == "action" and sim == "room":
+            if s.name == "action" and sim in ("room", "arena"):
                 full[keep_worlds:, :, 2] = 2      # neutral turn for the rest
             in_t[s.name].copy_(full)
         torch.cuda.synchronize()
@@ -73,3 +73,17 @@ def test_room_8192_worlds_is_deterministic_and_finite():
     for k in a:
         assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
         assert np.isfinite(a[k].astype(np.float64)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not runner.available("arena"), reason="oracle/_ref not built")
+def test_arena_4096_worlds_prefix_equals_reference():
+    # configs[2]: 4096 worlds / GPU.  Worlds [0, 48) of the 4096-world GPU run must equal
+    # a 48-world run of the reference CPU backend bit for bit (an episode reset inside).
+    W, keep, steps = 4096, 48, 70
+    cfg = {"episode_len": 45, "seed": 11}
+    ins = make_inputs("arena", keep, steps, seed=77)
+    ref, _ = runner.run_reference(SIMS["arena"], keep, steps, ins, cfg, workers=4)
+    got = _rollout_prefix("arena", W, steps, ins, cfg, keep)
+    for k in got:
+        assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), k

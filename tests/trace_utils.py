@@ -36,6 +36,16 @@ def make_inputs(sim: str, num_worlds: int, num_steps: int, seed: int = 0) -> Dic
             "reset": (rng.random((num_steps, num_worlds, 1)) < 0.005).astype(np.int32),
             "action": act.astype(np.int32),
         }
+    if sim == "arena":
+        shape = (num_steps, num_worlds, 6)
+        amount = np.where(rng.random(shape) < 0.6, 3, rng.integers(0, 4, size=shape))
+        angle = np.where(rng.random(shape) < 0.6, 0, rng.integers(0, 8, size=shape))
+        act = np.stack([amount, angle, rng.integers(0, 5, size=shape),
+                        (rng.random(shape) < 0.15).astype(np.int64)], axis=-1)
+        return {
+            "reset": (rng.random((num_steps, num_worlds, 1)) < 0.004).astype(np.int32),
+            "action": act.astype(np.int32),
+        }
     if sim in ("balls", "balls_many"):
         return {}          # physics only: no inputs
     raise KeyError(sim)
