@@ -538,24 +538,26 @@ struct AABB {
         return o;
     }
 
-    // Slab test, reference math.inl:1698-1735.
+    // Slab test, reference math.inl:1670-1735 ("max of mins, min of maxes" with
+    // fminf / fmaxf, which skip NaNs, and a NON-strict final comparison): kept
+    // expression for expression -- the NaN / infinity / equality cases decide
+    // which leaves a grazing ray visits.
     MB2_HD bool rayIntersects(Vector3 ray_o, Diag3x3 inv_ray_d,
                               float ray_t_min, float ray_t_max,
                               float &hit_t, float &far_t)
     {
-        float t_min = ray_t_min, t_max = ray_t_max;
-        for (int i = 0; i < 3; i++) {
-            float inv_d = inv_ray_d[i];
-            float t0 = (pMin[i] - ray_o[i]) * inv_d;
-            float t1 = (pMax[i] - ray_o[i]) * inv_d;
-            if (inv_d < 0.f) { float t = t0; t0 = t1; t1 = t; }
-            t_min = t0 > t_min ? t0 : t_min;
-            t_max = t1 < t_max ? t1 : t_max;
-            if (t_max <= t_min) return false;
+        Vector3 t_lower = inv_ray_d * (pMin - ray_o);
+        Vector3 t_upper = inv_ray_d * (pMax - ray_o);
+        Vector3 mins = Vector3::min(t_lower, t_upper);
+        Vector3 maxes = Vector3::max(t_lower, t_upper);
+        float t_box_min = fmaxf(mins.x, fmaxf(mins.y, fmaxf(mins.z, ray_t_min)));
+        float t_box_max = fminf(maxes.x, fminf(maxes.y, fminf(maxes.z, ray_t_max)));
+        if (t_box_min <= t_box_max) {
+            hit_t = t_box_min;
+            far_t = t_box_max;
+            return true;
         }
-        hit_t = t_min;
-        far_t = t_max;
-        return true;
+        return false;
     }
     MB2_HD bool rayIntersects(Vector3 ray_o, Diag3x3 inv_ray_d,
                               float ray_t_min, float ray_t_max)

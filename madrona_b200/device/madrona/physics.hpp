@@ -549,11 +549,12 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
     // Walking is latency bound, so a popped node is read once, whole (28
     // independent loads), and its four slab tests run side by side.  The
     // reference tests child i against the t_max current at that moment
-    // (src/physics/broadphase.cpp traceRay + math.inl:1698-1735); that test
-    // factors exactly into a part independent of t_max (the slab intervals
-    // overlap) and "t_max > entry distance", so the first part is evaluated at
-    // pop time and the second when the child's turn comes: same decisions, same
-    // visit order (pop node, children 0..3 in order), same floats.
+    // (src/physics/broadphase.cpp:658-724 + math.inl:1670-1696):
+    //   max(mins.x, mins.y, mins.z, 0) <= min(maxes.x, maxes.y, maxes.z, t_max)
+    // with NaN-skipping fminf / fmaxf.  t_max is never NaN, so the right side
+    // equals fminf(min(maxes...), t_max): the box part (entry, exit) is
+    // evaluated at pop time, the comparison when the child's turn comes -- same
+    // decisions, same visit order (pop node, children 0..3 in order).
     const unsigned peers = __activemask();
     int32_t stack[32];
     stack[0] = 0;
@@ -561,36 +562,20 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
     unsigned pending = 0;                 // slots of the current node still to visit
     int32_t kid0 = -1, kid1 = -1, kid2 = -1, kid3 = -1;
     float ent0 = 0.f, ent1 = 0.f, ent2 = 0.f, ent3 = 0.f;
+    float ext0 = 0.f, ext1 = 0.f, ext2 = 0.f, ext3 = 0.f;
     bool walking = true;
     Entity closest = Entity::none();
     math::Vector3 closest_normal { 0, 0, 0 };
 
-    auto slab = [&](const mb2::BVHNode &node, int i, float *entry) {
-        float t_near = 0.f, t_far = INFINITY;
-        bool overlap = true;
-        {
-            float t0 = (node.minX[i] - o.x) * inv_d.d0, t1 = (node.maxX[i] - o.x) * inv_d.d0;
-            if (inv_d.d0 < 0.f) { float t = t0; t0 = t1; t1 = t; }
-            t_near = t0 > t_near ? t0 : t_near;
-            t_far = t1 < t_far ? t1 : t_far;
-            overlap = overlap && !(t_far <= t_near);
-        }
-        {
-            float t0 = (node.minY[i] - o.y) * inv_d.d1, t1 = (node.maxY[i] - o.y) * inv_d.d1;
-            if (inv_d.d1 < 0.f) { float t = t0; t0 = t1; t1 = t; }
-            t_near = t0 > t_near ? t0 : t_near;
-            t_far = t1 < t_far ? t1 : t_far;
-            overlap = overlap && !(t_far <= t_near);
-        }
-        {
-            float t0 = (node.minZ[i] - o.z) * inv_d.d2, t1 = (node.maxZ[i] - o.z) * inv_d.d2;
-            if (inv_d.d2 < 0.f) { float t = t0; t0 = t1; t1 = t; }
-            t_near = t0 > t_near ? t0 : t_near;
-            t_far = t1 < t_far ? t1 : t_far;
-            overlap = overlap && !(t_far <= t_near);
-        }
-        *entry = t_near;
-        return overlap;
+    auto slab = [&](const mb2::BVHNode &node, int i, float *entry, float *exit) {
+        const float lx = inv_d.d0 * (node.minX[i] - o.x), ux = inv_d.d0 * (node.maxX[i] - o.x);
+        const float ly = inv_d.d1 * (node.minY[i] - o.y), uy = inv_d.d1 * (node.maxY[i] - o.y);
+        const float lz = inv_d.d2 * (node.minZ[i] - o.z), uz = inv_d.d2 * (node.maxZ[i] - o.z);
+        *entry = fmaxf(fminf(lx, ux), fmaxf(fminf(ly, uy), fmaxf(fminf(lz, uz), 0.f)));
+        const float far_z = fmaxf(lz, uz);
+        *exit = fminf(fmaxf(lx, ux), fminf(fmaxf(ly, uy), far_z));
+        // necessary for the full test whatever t_max is (an all-NaN exit passes)
+        return !(*entry > *exit);
     };
 
     while (__any_sync(peers, walking)) {
@@ -604,8 +589,8 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
                 const mb2::BVHNode &node = s_.nodes[stack[--stack_size]];
                 kid0 = node.children[0]; kid1 = node.children[1];
                 kid2 = node.children[2]; kid3 = node.children[3];
-                const bool in0 = slab(node, 0, &ent0), in1 = slab(node, 1, &ent1);
-                const bool in2 = slab(node, 2, &ent2), in3 = slab(node, 3, &ent3);
+                const bool in0 = slab(node, 0, &ent0, &ext0), in1 = slab(node, 1, &ent1, &ext1);
+                const bool in2 = slab(node, 2, &ent2, &ext2), in3 = slab(node, 3, &ent3, &ext3);
                 pending = ((kid0 != -1 && in0) ? 1u : 0u) | ((kid1 != -1 && in1) ? 2u : 0u) |
                           ((kid2 != -1 && in2) ? 4u : 0u) | ((kid3 != -1 && in3) ? 8u : 0u);
                 continue;
@@ -613,8 +598,9 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
             const int i = __ffs((int)pending) - 1;
             pending &= pending - 1;
             const float entry = i == 0 ? ent0 : (i == 1 ? ent1 : (i == 2 ? ent2 : ent3));
+            const float exit = i == 0 ? ext0 : (i == 1 ? ext1 : (i == 2 ? ext2 : ext3));
             const int32_t child = i == 0 ? kid0 : (i == 1 ? kid1 : (i == 2 ? kid2 : kid3));
-            if (t_max <= entry) continue;
+            if (!(entry <= fminf(exit, t_max))) continue;
             if (child & 0x80000000) {
                 leaf_idx = child & 0x7fffffff;
                 break;

@@ -21,6 +21,12 @@ static void pf(const char *tag, float v)
     memcpy(&b, &v, 4);
     printf("%s %08x\n", tag, b);
 }
+static uint32_t bits(float v)
+{
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    return b;
+}
 static void pv(const char *tag, Vector3 v) { pf(tag, v.x); pf(tag, v.y); pf(tag, v.z); }
 static void pq(const char *tag, Quat q) { pf(tag, q.w); pf(tag, q.x); pf(tag, q.y); pf(tag, q.z); }
 
@@ -110,6 +116,24 @@ int main()
         e.expand(a); e.expand(b); e.expand(c);
         pv("exp_min", e.pMin); pv("exp_max", e.pMax);
         pv("div", a / 3.f); pv("div2", 2.f / b);
+
+        // slab test incl. its edge cases: axis-parallel rays (infinite inverse
+        // direction), origins exactly on a box plane (0 * inf = NaN), touching
+        // intervals (t_box_min == t_box_max)
+        for (int variant = 0; variant < 6; variant++) {
+            Vector3 o = c, d = (b - c).normalize();
+            if (variant == 1) d = Vector3 { d.x, d.y, 0.f };
+            if (variant == 2) { d = Vector3 { 0.f, 1.f, 0.f }; o.x = box.pMin.x; }
+            if (variant == 3) { d = Vector3 { 1.f, 0.f, 0.f }; o.z = box.pMax.z; o.x = box.pMin.x - 1.f; }
+            if (variant == 4) { o = box.pMax; d = Vector3 { 1.f, 1.f, 1.f }; }
+            if (variant == 5) { o = box.pMin - Vector3 { 1.f, 0.f, 0.f }; d = Vector3 { 1.f, 0.f, 0.f }; }
+            Diag3x3 inv_d = Diag3x3::fromVec(d).inv();
+            float t_hit = -1.f, t_far = -1.f;
+            float t_max = variant == 5 ? 1.f : 100.f;
+            bool hit = box.rayIntersects(o, inv_d, 0.f, t_max, t_hit, t_far);
+            bool hit2 = box.rayIntersects(o, inv_d, 0.f, t_max);
+            printf("ray %d %d %08x %08x\n", (int)hit, (int)hit2, hit ? bits(t_hit) : 0u, hit ? bits(t_far) : 0u);
+        }
     }
     return 0;
 }

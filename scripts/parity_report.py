@@ -1,4 +1,4 @@
-"""Dev tool: room fixture, B200 engine vs live reference CPU backend, per-step drift."""
+"""Dev tool: a fixture (argv[3], default room), B200 engine vs live reference CPU backend, per-step drift."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,10 +9,11 @@ from trace_utils import make_inputs, rollout_gpu
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 250
+sim = sys.argv[3] if len(sys.argv) > 3 else "room"
 cfg = {"episode_len": 100, "seed": 1}
-ins = make_inputs("room", W, steps, seed=5)
-ref, _ = run_reference(SIMS["room"], W, steps, ins, cfg, workers=1)
-got, nk = rollout_gpu("room", W, steps, ins, cfg)
+ins = make_inputs(sim, W, steps, seed=5)
+ref, _ = run_reference(SIMS[sim], W, steps, ins, cfg, workers=1)
+got, nk = rollout_gpu(sim, W, steps, ins, cfg)
 print("kernels per step", nk)
 for k in ref:
     r, g = ref[k], got[k]
@@ -36,3 +37,7 @@ for k in ref:
             err = np.abs(r - g).reshape(r.shape[0], -1).max(axis=1)
             first = next((t for t, e in enumerate(err) if e > 0), None)
             print(k, "max abs err", float(err.max()), "first nonzero step", first)
+            if first is not None:
+                idx = np.argwhere(r[first] != g[first])[:4]
+                for i in idx:
+                    print("    step", first, "at", i.tolist(), "ref", r[first][tuple(i)], "got", g[first][tuple(i)])
