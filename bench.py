@@ -6,11 +6,18 @@
 A "step" = one pass of the simulator's step task graph over all worlds
 (MWCudaExecutor::run equivalent).  One process per GPU (torchrun for N>1);
 worlds shard across ranks with no data-path collective, the only exchange is
-the NCCL all_gather of the exported reward/done tensors after each step
-(SURVEY.md 8e).  Prints ONE JSON line on rank 0.
+the gather of the exported reward/done tensors after each step:
+one NVLink peer-store kernel per rank per step into every peer's symmetric
+buffer (madrona_b200/csrc/peer_gather.cu), consumed one step later so it
+overlaps the next step graph; `--gather nccl` selects ONE packed
+all_gather_into_tensor per step on a side stream instead.  Prints ONE JSON
+line on rank 0.
 
-  value     device-timed (CUDA events on the launching stream, max over ranks)
-            throughput with inputs already resident in HBM.
+  value     device-timed throughput with inputs already resident in HBM:
+            K steps, each bracketed by CUDA events on the launching stream;
+            the time is the SUM of the per-step intervals (the 256 MiB L2 flush
+            between steps is excluded), max over ranks.  `run_loop` next to it
+            is the plain wall clock of K back-to-back run() calls (no flush).
   e2e       same metric through the C ABI with HOST buffers: every step copies
             the actions H2D from pinned memory and reads rewards+dones back D2H.
   roofline  dominant node of the step (per-node CUDA-event timing inside this
@@ -109,6 +116,9 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+N_ACT = 16   # length of the action cycle both arms replay
+
+
 def make_actions(desc, sim, W, steps, seed):
     rng = np.random.default_rng(seed)
     out = {}
@@ -148,8 +158,10 @@ ROOFLINE_NOTES = {
 }
 
 
-def run_reference_arm(args, wl):
-    """The reference's own CPU implementation of the path on the host cores."""
+def run_reference_arm(args, wl, reps=3):
+    """The reference's own CPU implementation of the path on the host cores,
+    replaying the SAME seeded action tensor as the GPU arm (its first
+    `ref_worlds` worlds, the same 16-step cycle)."""
     from oracle import runner
     from sims import SIMS
 
@@ -168,14 +180,29 @@ def run_reference_arm(args, wl):
     steps = getattr(args, "ref_steps", None) or max(args.steps + args.warmup, wl.get("ref_steps", 2000))
     if not runner.available(desc.name):
         return None
-    t0 = time.time()
-    _, timing = runner.run_reference(desc, W, steps, None, wl["cfg"], workers=cores, want_outputs=False)
-    wall = time.time() - t0
-    return {"value": timing["steps_per_sec"], "unit": "env-steps/s", "cores": cores, "kind": "reference",
-            "sample": f"{desc.name}: {W} worlds x {steps} steps, reference TaskGraphExecutor "
-                      f"numWorkers={cores} (oracle/_ref, g++ -O2 -march=x86-64-v3), zero actions, "
-                      f"{timing['seconds']:.2f}s in run() / {wall:.1f}s wall",
-            "ms_per_step": timing["seconds"] / steps * 1e3, "worlds": W}
+    cycle = make_actions(desc, wl["sim"], wl["worlds"], N_ACT, seed=1000)
+    inputs = None
+    if desc.inputs:
+        idx = np.arange(steps) % N_ACT
+        inputs = {k: np.ascontiguousarray(v[idx][:, :W]) for k, v in cycle.items()}
+    runs, walls = [], []
+    for _ in range(reps):
+        t0 = time.time()
+        _, timing = runner.run_reference(desc, W, steps, inputs, wl["cfg"], workers=cores, want_outputs=False)
+        walls.append(time.time() - t0)
+        runs.append(timing)
+    order = sorted(range(reps), key=lambda i: runs[i]["steps_per_sec"])
+    med = runs[order[reps // 2]]
+    vals = [r["steps_per_sec"] for r in runs]
+    return {"value": med["steps_per_sec"], "unit": "env-steps/s", "cores": cores, "kind": "reference",
+            "sample": f"{desc.name}: {W} worlds x {steps} steps (RAM-bounded: the CPU backend's tmp allocator is "
+                      f"32 MiB/world, include/madrona/state.hpp:362), reference TaskGraphExecutor "
+                      f"numWorkers={cores} (oracle/_ref, g++ -O2 -march=x86-64-v3), same seeded random actions as "
+                      f"the GPU arm (first {W} worlds, {N_ACT}-step cycle); median of {reps} runs, "
+                      f"min/max {min(vals):.0f}/{max(vals):.0f} env-steps/s, "
+                      f"{med['seconds']:.2f}s in run() / {walls[order[reps // 2]]:.1f}s wall",
+            "runs": vals,
+            "ms_per_step": med["seconds"] / steps * 1e3, "worlds": W}
 
 
 def main():
@@ -188,6 +215,8 @@ def main():
     ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (default: workload's)")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: NVLink peer-store gather kernel (default) or one packed NCCL all_gather per step")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.worlds:
@@ -213,7 +242,7 @@ def main():
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
                 "config": dict(config, worlds_per_gpu=res["worlds"]),
-                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "runs")},
                 "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -249,10 +278,8 @@ def main():
     in_t = {s.name: ex.tensor(s.slot, s.dtype, (W,) + s.per_world) for s in desc.inputs}
     fixed_out = [s for s in desc.outputs if not s.dynamic and s.name in ("reward", "done")]
     out_t = {s.name: ex.tensor(s.slot, s.dtype, (W,) + s.per_world) for s in fixed_out}
-    gathered = {k: torch.empty((world_size * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
-                for k, v in out_t.items()} if world_size > 1 else {}
 
-    n_act = 16
+    n_act = N_ACT
     host_actions = make_actions(desc, wl["sim"], W, n_act, seed=1000 + rank)
     dev_actions = {k: torch.from_numpy(v).to(dev) for k, v in host_actions.items()}
     pinned_actions = {k: torch.from_numpy(v).pin_memory() for k, v in host_actions.items()}
@@ -260,6 +287,68 @@ def main():
 
     stream = torch.cuda.current_stream()
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- N > 1: the gather of the exported reward / done columns
+    gather_kind = None
+    pg = None
+    nccl = None
+    if world_size > 1 and out_t:
+        if args.gather == "p2p":
+            try:
+                pg = ex.peerGather([s.slot for s in fixed_out], [(W,) + s.per_world for s in fixed_out],
+                                   [s.dtype for s in fixed_out], world_size, rank)
+                sharding.connect_peer_gather(pg)
+                gather_kind = "p2p-push: one NVLink peer-store kernel per rank per step into every peer's " \
+                              "symmetric buffer, consumed one step later (peer_gather.cu)"
+            except Exception as e:      # e.g. cudaIpc refused by the container
+                pg = None
+                gather_kind = f"nccl (p2p unavailable: {e})"
+        ok = torch.tensor([1 if pg is not None or args.gather == "nccl" else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 or args.gather == "nccl":
+            if pg is not None:
+                pg.close()
+                pg = None
+            # ONE packed all_gather per step on a side stream, double buffered
+            pack_elems = sum(t.numel() for t in out_t.values())   # all 4-byte columns
+            nccl = dict(side=torch.cuda.Stream(device=dev),
+                        pack=[torch.empty(pack_elems, dtype=torch.int32, device=dev) for _ in range(2)],
+                        out=[torch.empty(world_size * pack_elems, dtype=torch.int32, device=dev) for _ in range(2)],
+                        done_ev=[torch.cuda.Event() for _ in range(2)],
+                        packed_ev=[torch.cuda.Event() for _ in range(2)])
+            gather_kind = gather_kind or "nccl: one packed all_gather_into_tensor per step on a side stream, " \
+                                         "double buffered"
+            # warm NCCL (channel setup, first-use allocations) outside the --warmup budget
+            for _ in range(64):
+                dist.all_gather_into_tensor(nccl["out"][0], nccl["pack"][0])
+            torch.cuda.synchronize()
+    step_counter = [0]
+
+    def gather_step():
+        k = step_counter[0]
+        step_counter[0] += 1
+        if pg is not None:
+            pg.push(stream)
+            if k >= 1:
+                pg.wait(stream)       # step k-1 of every rank has landed here
+                pg.release(stream)    # (a learner would read pg.tensor((k-1) & 1, i) in between)
+        elif nccl is not None:
+            par = k & 1
+            nccl["done_ev"][par].record(stream)
+            with torch.cuda.stream(nccl["side"]):
+                nccl["side"].wait_event(nccl["done_ev"][par])
+                torch.cat([t.reshape(-1).view(torch.int32) for t in out_t.values()], out=nccl["pack"][par])
+                nccl["packed_ev"][par].record(nccl["side"])
+                dist.all_gather_into_tensor(nccl["out"][par], nccl["pack"][par])
+            # the next step graph may overwrite the columns once they are packed
+            stream.wait_event(nccl["packed_ev"][par])
+
+    def gather_drain():
+        if pg is not None and step_counter[0] >= 1:
+            pg.wait(stream)
+            pg.release(stream)
+        if nccl is not None:
+            stream.wait_stream(nccl["side"])
 
     def one_step(i, host_io=False):
         if host_io:
@@ -272,8 +361,7 @@ def main():
         if render_graph is not None:
             ex.runAsync(render_graph, stream)
         if world_size > 1:
-            for k, t in out_t.items():
-                sharding.gather_exported(t, out=gathered[k])
+            gather_step()
         if host_io:
             for k, t in out_t.items():
                 pinned_out[k].copy_(t, non_blocking=True)
@@ -297,18 +385,40 @@ def main():
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        per_step = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+        total_ms = float(per_step.sum())
+        t = torch.tensor([total_ms, float(per_step.min()), float(np.median(per_step)), float(per_step.max())],
+                         dtype=torch.float64, device=dev)
         if world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+            allr = [torch.empty_like(t) for _ in range(world_size)]
+            dist.all_gather(allr, t)
+            stats = [[round(float(v), 4) for v in r.tolist()] for r in allr]
+            total_ms = max(r[0] for r in stats)
+        else:
+            stats = [[round(float(v), 4) for v in t.tolist()]]
+        return total_ms, stats
+
+    def run_loop_wall():
+        """Plain wall clock of K back-to-back run() calls (launch + stream sync each), no flush."""
+        for i in range(3):
+            ex.run(graph)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            ex.run(graph)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    total_ms = timed(host_io=False)
-    e2e_ms = timed(host_io=True)
+    total_ms, rank_stats = timed(host_io=False)
+    e2e_ms, e2e_rank_stats = timed(host_io=True)
+    if world_size > 1:
+        gather_drain()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    wall_ms = run_loop_wall() if world_size == 1 else None
 
     h2d = sum(int(np.prod(v.shape[1:])) * v.dtype.itemsize for v in host_actions.values())
     d2h = sum(t.numel() * t.element_size() for t in out_t.values())
@@ -370,8 +480,10 @@ def main():
             small = argparse.Namespace(steps=0, warmup=0, ref_steps=wl.get("ref_steps", 2000))
             res = run_reference_arm(small, wl)
             if res:
-                cpu_base = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                cpu_base = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "runs")}
 
+    if pg is not None:
+        pg.close()
     ex.close()
     if rank == 0:
         total_worlds = W * world_size
@@ -390,6 +502,16 @@ def main():
             "data": "synthetic",
             "config": dict(config, l2="flushed between steps (256 MiB write)" if flush is not None
                            else "not flushed"),
+            "timing": "sum of per-step CUDA-event intervals on the launching stream (L2 flush between steps "
+                      "excluded), max over ranks",
+            "run_loop": None if wall_ms is None else {
+                "value": total_worlds * args.steps / (wall_ms * 1e-3), "unit": "env-steps/s",
+                "ms_per_step": wall_ms / args.steps,
+                "what": "wall clock of K back-to-back run() calls (graph launch + stream sync), no L2 flush"},
+            "gather": None if world_size == 1 else {
+                "kind": gather_kind, "bytes_per_rank_per_step": d2h,
+                "per_rank_ms [total, step min, median, max]": rank_stats,
+                "per_rank_ms_e2e": e2e_rank_stats},
             "clocks": clocks,
             "e2e": {"value": total_worlds * args.steps / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -146,6 +146,36 @@ int64_t mb2_profile_nodes(mb2_executor *exec, const uint32_t *taskgraph_ids,
                           uint32_t num_taskgraphs, uint32_t reps,
                           char *json_out, uint64_t json_capacity);
 
+/* ---- multi-GPU gather of exported columns ------------------
+ * No reference counterpart (the reference is single-GPU, mw_gpu.hpp:122):
+ * worlds shard across GPUs, one process per GPU, and the only exchange is the
+ * gather of exported tensors (observations, rewards, dones) into the
+ * world-major tensor every rank sees.  Instead of one NCCL all_gather per
+ * tensor per step, each rank pushes its slices straight into every peer's
+ * symmetric buffer with NVLink peer stores from one kernel (peer_gather.cu).
+ *
+ *   g = mb2_peer_gather_create(exec, slots, n, bytes_per_slot, world_size, rank)
+ *   mb2_peer_gather_local_handle(g, h)      -> 128 opaque bytes; exchange them
+ *   mb2_peer_gather_connect(g, all)         <- world_size * 128 bytes, rank order
+ *   per step:  run_async(graph); push_async(g); ... wait_async(g); read
+ *              mb2_peer_gather_buffer(g, step & 1, i); release_async(g)
+ * push / wait / release each advance their own step counter (kept on the
+ * device), so they are CUDA-graph friendly.  bytes_per_slot[i] = bytes of ONE
+ * rank's column (identical on all ranks, multiple of 4); buffer i of a parity
+ * is [world_size][bytes_per_slot[i]], i.e. the world-major gathered column. */
+typedef struct mb2_peer_gather mb2_peer_gather;
+#define MB2_PEER_GATHER_HANDLE_BYTES 128
+mb2_peer_gather *mb2_peer_gather_create(mb2_executor *exec, const int64_t *slots,
+                                        uint32_t num_slots, const uint64_t *bytes_per_slot,
+                                        uint32_t world_size, uint32_t rank);
+int mb2_peer_gather_local_handle(mb2_peer_gather *gather, void *handle_out);
+int mb2_peer_gather_connect(mb2_peer_gather *gather, const void *all_handles);
+int mb2_peer_gather_push_async(mb2_peer_gather *gather, void *cuda_stream);
+int mb2_peer_gather_wait_async(mb2_peer_gather *gather, void *cuda_stream);
+int mb2_peer_gather_release_async(mb2_peer_gather *gather, void *cuda_stream);
+void *mb2_peer_gather_buffer(mb2_peer_gather *gather, uint32_t parity, uint32_t slot_index);
+void mb2_peer_gather_destroy(mb2_peer_gather *gather);
+
 /* Version string. */
 const char *mb2_version(void);
 

@@ -141,15 +141,7 @@ Entity Context::makeEntity(uint32_t archetype_id)
     mwGPU::unlockCache(cache);
 
     int32_t row = mwGPU::appendRow(tbl, archetype_id);
-    if (row < 0 || e.id < 0) {
-        if (e.id >= 0) {
-            // no row for it: hand the ID back instead of leaking it
-            mwGPU::lockCache(cache);
-            mwGPU::releaseEntityLocked(S, cache, e.id);
-            mwGPU::unlockCache(cache);
-        }
-        return Entity::none();
-    }
+    if (row < 0 || e.id < 0) return Entity::none();
 
     ((Entity *)tbl.columns[0])[row] = e;
     ((WorldID *)tbl.columns[1])[row] = world_id_;

@@ -194,8 +194,12 @@ inline int32_t appendRow(mb2::TableDesc &tbl, uint32_t archetype_id)
     base = __shfl_sync(peers, base, leader);
     int32_t row = base + rank;
     if (row >= tbl.capacity) {
+        // The step is reported as failed (run() returns the error); the caller
+        // still gets a row INSIDE the allocation -- the table's last one, shared
+        // by every overflowing append -- so simulator code that goes on to
+        // initialise "its" new entity cannot write out of bounds.
         raiseError(mb2::ErrTableOverflow, archetype_id);
-        return -1;
+        return tbl.capacity - 1;
     }
     return row;
 }

@@ -35,6 +35,14 @@ EXPORTED_SYMBOLS = [
     "mb2_jit_precompile",
     "mb2_profile_nodes",
     "mb2_version",
+    "mb2_peer_gather_create",
+    "mb2_peer_gather_local_handle",
+    "mb2_peer_gather_connect",
+    "mb2_peer_gather_push_async",
+    "mb2_peer_gather_wait_async",
+    "mb2_peer_gather_release_async",
+    "mb2_peer_gather_buffer",
+    "mb2_peer_gather_destroy",
 ]
 
 
@@ -138,6 +146,21 @@ def load_library() -> ctypes.CDLL:
     lib.mb2_profile_nodes.restype = ctypes.c_int64
     lib.mb2_version.argtypes = []
     lib.mb2_version.restype = ctypes.c_char_p
+    lib.mb2_peer_gather_create.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_uint32,
+                                           ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint32, ctypes.c_uint32]
+    lib.mb2_peer_gather_create.restype = vp
+    lib.mb2_peer_gather_local_handle.argtypes = [vp, ctypes.c_char_p]
+    lib.mb2_peer_gather_local_handle.restype = ctypes.c_int
+    lib.mb2_peer_gather_connect.argtypes = [vp, ctypes.c_char_p]
+    lib.mb2_peer_gather_connect.restype = ctypes.c_int
+    for name in ("push", "wait", "release"):
+        fn = getattr(lib, f"mb2_peer_gather_{name}_async")
+        fn.argtypes = [vp, vp]
+        fn.restype = ctypes.c_int
+    lib.mb2_peer_gather_buffer.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32]
+    lib.mb2_peer_gather_buffer.restype = vp
+    lib.mb2_peer_gather_destroy.argtypes = [vp]
+    lib.mb2_peer_gather_destroy.restype = None
     _LIB = lib
     return lib
 
@@ -334,6 +357,12 @@ class MWCudaExecutor:
         from .tensor import Tensor
         return Tensor(self.getExported(slot), type, dimensions, gpu_id=self.gpu_id)
 
+    def peerGather(self, slots, shapes, dtypes, world_size: int, rank: int):
+        """NVLink peer-store gather of fixed-size exported columns across the ranks of a
+        node (include/madrona_b200.h, peer_gather.cu).  slots / shapes / dtypes describe
+        this rank's columns; returns a PeerGather whose handle must be exchanged."""
+        return PeerGather(self, slots, shapes, dtypes, world_size, rank)
+
     def close(self) -> None:
         if self._h:
             self._lib.mb2_executor_destroy(self._h)
@@ -344,3 +373,64 @@ class MWCudaExecutor:
             self.close()
         except Exception:
             pass
+
+
+class PeerGather:
+    """Symmetric-buffer gather: every rank pushes its exported columns into every
+    peer's buffer with NVLink peer stores (one kernel per step), consumers wait on
+    per-rank step flags.  See include/madrona_b200.h for the protocol."""
+
+    HANDLE_BYTES = 128
+
+    def __init__(self, ex: "MWCudaExecutor", slots, shapes, dtypes, world_size: int, rank: int):
+        import numpy as np
+        self._lib = ex._lib
+        self._ex = ex
+        self.world_size, self.rank = int(world_size), int(rank)
+        self.shapes = [tuple(int(d) for d in s) for s in shapes]
+        self.dtypes = list(dtypes)
+        nbytes = [int(np.prod(s)) * np.dtype(d).itemsize for s, d in zip(self.shapes, self.dtypes)]
+        c_slots = (ctypes.c_int64 * len(slots))(*[int(s) for s in slots])
+        c_bytes = (ctypes.c_uint64 * len(slots))(*nbytes)
+        self._h = self._lib.mb2_peer_gather_create(ex._h, c_slots, len(slots), c_bytes, self.world_size, self.rank)
+        if not self._h:
+            raise MadronaB200Error(_last_error(self._lib))
+
+    def local_handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+        if self._lib.mb2_peer_gather_local_handle(self._h, buf) != 0:
+            raise MadronaB200Error(_last_error(self._lib))
+        return buf.raw
+
+    def connect(self, all_handles: Sequence[bytes]) -> None:
+        blob = b"".join(all_handles)
+        assert len(blob) == self.HANDLE_BYTES * self.world_size
+        if self._lib.mb2_peer_gather_connect(self._h, blob) != 0:
+            raise MadronaB200Error(_last_error(self._lib))
+
+    def _call(self, name, stream):
+        s = getattr(stream, "cuda_stream", stream)
+        if getattr(self._lib, f"mb2_peer_gather_{name}_async")(self._h, ctypes.c_void_p(int(s))) != 0:
+            raise MadronaB200Error(f"peer gather {name} launch failed")
+
+    def push(self, stream):
+        self._call("push", stream)
+
+    def wait(self, stream):
+        self._call("wait", stream)
+
+    def release(self, stream):
+        self._call("release", stream)
+
+    def tensor(self, parity: int, index: int):
+        """World-major gathered column [world_size * W_local, ...] of a parity (zero copy)."""
+        import torch
+        shape = (self.world_size * self.shapes[index][0],) + self.shapes[index][1:]
+        ptr = self._lib.mb2_peer_gather_buffer(self._h, int(parity), int(index))
+        view = _CudaView(ptr, shape, _TYPESTR[self.dtypes[index]])
+        return torch.as_tensor(view, device=f"cuda:{self._ex.gpu_id}")
+
+    def close(self):
+        if self._h:
+            self._lib.mb2_peer_gather_destroy(self._h)
+            self._h = None

@@ -51,3 +51,16 @@ def local_slice(global_tensor, rank: Optional[int] = None, world_size: Optional[
         world_size = dist.get_world_size(group)
     first, count = shard_range(global_tensor.shape[0], world_size, rank)
     return global_tensor[first:first + count]
+
+
+def connect_peer_gather(gather, group=None):
+    """Exchange the cudaIpc handles of a madrona_b200.PeerGather over the process group
+    (host-side plumbing, works with any backend) and map every peer's buffer."""
+    import torch.distributed as dist
+
+    world_size = dist.get_world_size(group)
+    handles = [None] * world_size
+    dist.all_gather_object(handles, gather.local_handle(), group=group)
+    gather.connect(handles)
+    dist.barrier(group=group)
+    return gather

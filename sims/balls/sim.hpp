@@ -27,7 +27,13 @@ using madrona::phys::ExternalForce;
 using madrona::phys::ExternalTorque;
 
 constexpr int32_t kNumWalls = 4;
-#ifdef BALLS_MANY
+#if defined(BALLS_MANY) && BALLS_MANY == 2
+// build variant (GPU only): 145 bodies per world, beyond the engine's documented
+// per-world body cap -- the step must report the overflow, not corrupt memory
+constexpr int32_t kNumCubes = 10;
+constexpr int32_t kNumBalls = 130;
+constexpr float kPen = 12.f;
+#elif defined(BALLS_MANY)
 // build variant: 95 bodies per world (> 64: more than one word of the engine's
 // candidate-search leaf masks), a bigger pen
 constexpr int32_t kNumCubes = 10;

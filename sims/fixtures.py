@@ -200,6 +200,21 @@ SIMS: Dict[str, SimDesc] = {
         objects=_balls_objects,
         compile_flags=["-DBALLS_MANY=1"],
     ),
+    # GPU only: 145 bodies per world, past the per-world body cap (tests/test_cliffs.py)
+    "balls_cliff": SimDesc(
+        name="balls_cliff",
+        sources=[os.path.join(_ROOT, "balls", "sim.cpp")],
+        num_exports=4,
+        num_taskgraphs=1,
+        inputs=[],
+        outputs=[Slot(0, "body_pos", "float32", (145, 3))],
+        pack_config=lambda cfg: struct.pack("<Q", int(cfg.get("obj_mgr_ptr", 0))),
+        pack_init=lambda w, cfg: struct.pack("<I", int(cfg.get("seed", 0)) + w),
+        oracle_extra=lambda cfg: [int(cfg.get("seed", 0))],
+        defaults={"seed": 0},
+        objects=_balls_objects,
+        compile_flags=["-DBALLS_MANY=2"],
+    ),
     "gridworld": SimDesc(
         name="gridworld",
         sources=[os.path.join(_ROOT, "gridworld", "sim.cpp")],
@@ -238,8 +253,9 @@ def pack_world_inits(desc: SimDesc, num_worlds: int, cfg: Dict) -> bytes:
     return b"".join(desc.pack_init(w, cfg) for w in range(num_worlds))
 
 
-def make_executor(name: str, num_worlds: int, gpu_id: int = 0, **cfg):
-    """Build a madrona_b200.MWCudaExecutor for a fixture sim (needs a B200)."""
+def make_executor(name: str, num_worlds: int, gpu_id: int = 0, objects_fn=None, **cfg):
+    """Build a madrona_b200.MWCudaExecutor for a fixture sim (needs a B200).
+    objects_fn overrides the fixture's ObjectManager blob (same object indices)."""
     import madrona_b200 as mb
 
     desc = SIMS[name]
@@ -251,7 +267,7 @@ def make_executor(name: str, num_worlds: int, gpu_id: int = 0, **cfg):
         import numpy as np
         import torch
         from .objects import relocate
-        blob, relocs = desc.objects()
+        blob, relocs = (objects_fn or desc.objects)()
         dev_buf = torch.empty(len(blob) + 64, dtype=torch.uint8, device=f"cuda:{gpu_id}")
         base = (dev_buf.data_ptr() + 63) // 64 * 64
         fixed = relocate(blob, relocs, base)

@@ -293,3 +293,27 @@ def arena_objects() -> Tuple[bytes, List[int]]:
         dict(mesh="plane", meta=static),                                     # Plane
     ]
     return build_objects(specs)
+
+
+def ngon_prism_half_edge_mesh(n: int):
+    """Unit n-gon prism (2n vertices, n + 2 faces); n = 10 exceeds the engine's 16-vertex hull cap."""
+    ang = 2.0 * np.pi * np.arange(n) / n
+    ring = [(0.5 * np.cos(a), 0.5 * np.sin(a)) for a in ang]
+    v = np.array([[x, y, z] for z in (-0.5, 0.5) for (x, y) in ring], dtype=np.float32)
+    faces = [list(range(n)), list(range(n, 2 * n))] + [[i, (i + 1) % n, (i + 1) % n + n, i + n] for i in range(n)]
+    return build_half_edge_mesh(v, orient_faces(v, faces))
+
+
+def room_objects_big_hull() -> Tuple[bytes, List[int]]:
+    """sims/room objects with the Cube replaced by a 20-vertex prism (tests/test_cliffs.py)."""
+    box = box_half_edge_mesh()
+    static = _metadata(0.0, [0.0, 0.0, 0.0], 0.5, 0.5)
+    agent_inv_i = _box_inv_inertia(50.0, 1.0, 1.0, 1.5)
+    specs = [
+        dict(mesh=ngon_prism_half_edge_mesh(10),
+             meta=_metadata(np.float32(0.1), _box_inv_inertia(10.0, 1.5, 1.5, 1.5), 0.5, 0.75)),
+        dict(mesh=box, meta=static),
+        dict(mesh=box, meta=_metadata(np.float32(1.0 / 50.0), [0.0, 0.0, agent_inv_i[2]], 0.5, 0.5)),
+        dict(mesh="plane", meta=static),
+    ]
+    return build_objects(specs)
