@@ -322,16 +322,28 @@ def main():
             for _ in range(64):
                 dist.all_gather_into_tensor(nccl["out"][0], nccl["pack"][0])
             torch.cuda.synchronize()
+    p2p = None
+    if pg is not None:
+        p2p = dict(side=torch.cuda.Stream(device=dev), done_ev=[torch.cuda.Event() for _ in range(2)],
+                   pushed_ev=[torch.cuda.Event() for _ in range(2)])
     step_counter = [0]
 
     def gather_step():
         k = step_counter[0]
         step_counter[0] += 1
         if pg is not None:
-            pg.push(stream)
+            # the gather runs on a side stream: the compute stream only waits until its
+            # columns have been read (push done), not for the peers
+            par = k & 1
+            p2p["done_ev"][par].record(stream)
+            side = p2p["side"]
+            side.wait_event(p2p["done_ev"][par])
+            pg.push(side)
+            p2p["pushed_ev"][par].record(side)
             if k >= 1:
-                pg.wait(stream)       # step k-1 of every rank has landed here
-                pg.release(stream)    # (a learner would read pg.tensor((k-1) & 1, i) in between)
+                pg.wait(side)       # step k-1 of every rank has landed here
+                pg.release(side)    # (a learner would read pg.tensor((k-1) & 1, i) in between)
+            stream.wait_event(p2p["pushed_ev"][par])
         elif nccl is not None:
             par = k & 1
             nccl["done_ev"][par].record(stream)
@@ -345,8 +357,9 @@ def main():
 
     def gather_drain():
         if pg is not None and step_counter[0] >= 1:
-            pg.wait(stream)
-            pg.release(stream)
+            pg.wait(p2p["side"])
+            pg.release(p2p["side"])
+            stream.wait_stream(p2p["side"])
         if nccl is not None:
             stream.wait_stream(nccl["side"])
 

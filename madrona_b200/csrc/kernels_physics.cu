@@ -95,6 +95,7 @@ static_assert(sizeof(PMetadata) == 52, "RigidBodyMetadata layout");
 static_assert(sizeof(PCollisionPrimitive) == 56, "CollisionPrimitive layout");
 static_assert(sizeof(BVHNode) == 116, "BVH node layout");
 static_assert(sizeof(Contact) == 112, "contact layout");
+static_assert(sizeof(Candidate) == 16, "candidate layout");
 
 struct PVelocity {
     Vector3 linear;
@@ -423,6 +424,15 @@ __device__ void rebuildWorldBVH(WorldBVH &bvh)
         }
     }
     bvh.numTraversal = order_n;
+    for (i32 k = 0; k < order_n; k++) {
+        const i32 leaf = bvh.traversalOrder[k];
+        bvh.leafOrderPos[leaf] = k;
+        const u32 packed = bvh.leafParents[leaf];
+        const BVHNode &node = bvh.nodes[packed >> 2];
+        const int sub = (int)(packed & 3u);
+        bvh.orderedBoxes[2 * k] = PVec4 { node.minX[sub], node.minY[sub], node.minZ[sub], node.maxX[sub] };
+        bvh.orderedBoxes[2 * k + 1] = PVec4 { node.maxY[sub], node.maxZ[sub], __int_as_float(leaf), 0.f };
+    }
 }
 
 __device__ void refitLeaf(WorldBVH &bvh, i32 leaf);
@@ -467,6 +477,11 @@ __device__ void refitLeaf(WorldBVH &bvh, i32 leaf)
         prev = leaf_node.maxY[sub]; if (box.pMax.y > prev) { leaf_node.maxY[sub] = box.pMax.y; grew = true; }
         prev = leaf_node.maxZ[sub]; if (box.pMax.z > prev) { leaf_node.maxZ[sub] = box.pMax.z; grew = true; }
         if (!grew) return;
+        // keep the flat list in step with the slot box (only this leaf's thread writes either)
+        const i32 k = bvh.leafOrderPos[leaf];
+        float4 *flat = reinterpret_cast<float4 *>(bvh.orderedBoxes);
+        flat[2 * k] = make_float4(leaf_node.minX[sub], leaf_node.minY[sub], leaf_node.minZ[sub], leaf_node.maxX[sub]);
+        flat[2 * k + 1] = make_float4(leaf_node.maxY[sub], leaf_node.maxZ[sub], __int_as_float(leaf), 0.f);
     }
     i32 child = node_idx;
     node_idx = leaf_node.parentID;
@@ -494,6 +509,20 @@ __device__ __forceinline__ void rowRefit(const EngineState &S, const PhysicsStat
 {
     refitLeaf(worldBVH(S, P, w), bodyCol<i32>(S, b, PCLeafID, row));
 }
+
+// A body takes part in contact ordering unless writing it back is a no-op:
+// static (inverse mass / inertia forced to 0, so x is unchanged) AND its
+// rotation is a bitwise fixpoint of normalize() (so q is unchanged).  Decided
+// once per step by the candidate search (a fixpoint stays one: the solvers
+// write back normalize(q) == q; treating a body that BECAME a fixpoint during
+// the step as still mutable only adds ordering edges, never removes one).
+__device__ __forceinline__ bool rotationIsNormalizeFixpoint(Quat q)
+{
+    const Quat n = q.normalize();
+    return n.w == q.w && n.x == q.x && n.y == q.y && n.z == q.z;
+}
+
+constexpr u32 kUnknownSlot = 0x7fffu;
 
 // ---- candidate pairs: one warp per world, CPU iteration order -----------------------------
 
@@ -556,6 +585,7 @@ struct StagedLeaf {
     i32 row;
     u32 prims;          // 0 => stale entity / not a rigid body: never a partner
     u32 isStatic;
+    u32 slotInfo;       // (world body slot << 1) | mutable  (Candidate::slots)
 };
 
 struct CandidateScratch {
@@ -579,22 +609,41 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
 
     const i32 num_leaves = bvh.numTraversal;
     if (num_leaves > kMaxStagedLeaves) {
-        if (lane == 0) atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+        if (lane == 0) {
+            atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+            P.candCounts[w] = 0;
+        }
         return;
     }
+    // slot of a body inside its world's body list: archetypes ascending, rows in order
+    auto bodySlotInfo = [&](u32 arch, i32 row, bool is_static) -> u32 {
+        i32 slot_base = 0;
+        i32 slot = -1;
+        for (u32 bi = 0; bi < P.numBodyArchetypes; bi++) {
+            const TableDesc &bt = S.tables[P.bodies[bi].archetype];
+            if (P.bodies[bi].archetype == arch) {
+                slot = slot_base + (row - bt.worldOffsets[w]);
+                break;
+            }
+            slot_base += bt.worldCounts[w];
+        }
+        bool is_mutable = true;
+        if (is_static) is_mutable = !rotationIsNormalizeFixpoint(locCol<Quat>(S, P, arch, row, PCRotation));
+        const u32 s15 = (slot < 0 || slot >= (i32)kUnknownSlot) ? kUnknownSlot : (u32)slot;
+        return (s15 << 1) | (is_mutable ? 1u : 0u);
+    };
     // stage 1: lane k describes the k-th reported leaf
     for (i32 k = lane; k < num_leaves; k += 32) {
-        const i32 leaf = bvh.traversalOrder[k];
-        const u32 packed_parent = bvh.leafParents[leaf];
-        const BVHNode &node = bvh.nodes[packed_parent >> 2];
-        const int slot = (int)(packed_parent & 3u);
+        const float4 b0 = reinterpret_cast<const float4 *>(bvh.orderedBoxes)[2 * k];
+        const float4 b1 = reinterpret_cast<const float4 *>(bvh.orderedBoxes)[2 * k + 1];
+        const i32 leaf = __float_as_int(b1.z);
         StagedLeaf sl;
-        sl.box[0] = node.minX[slot]; sl.box[1] = node.minY[slot]; sl.box[2] = node.minZ[slot];
-        sl.box[3] = node.maxX[slot]; sl.box[4] = node.maxY[slot]; sl.box[5] = node.maxZ[slot];
+        sl.box[0] = b0.x; sl.box[1] = b0.y; sl.box[2] = b0.z;
+        sl.box[3] = b0.w; sl.box[4] = b1.x; sl.box[5] = b1.y;
         const u64 packed = bvh.leafEntities[leaf];
         sl.entityID = (i32)(u32)(packed >> 32);
         const u32 gen = (u32)(packed & 0xFFFFFFFFull);
-        sl.arch = 0; sl.row = 0; sl.prims = 0; sl.isStatic = 0;
+        sl.arch = 0; sl.row = 0; sl.prims = 0; sl.isStatic = 0; sl.slotInfo = 0;
         if (sl.entityID >= 0 && sl.entityID < S.entityCapacity) {
             const EntitySlot es = S.entitySlots[sl.entityID];
             const BodyArchetype *bb = es.gen == gen ? bodyOf(P, (u32)es.a) : nullptr;
@@ -603,6 +652,11 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
                 sl.row = es.b;
                 sl.isStatic = bodyCol<u32>(S, *bb, PCResponseType, es.b) == kRespStatic ? 1u : 0u;
                 sl.prims = objs.primCounts[bodyCol<i32>(S, *bb, PCObjectID, es.b)];
+                sl.slotInfo = bodySlotInfo(sl.arch, sl.row, sl.isStatic != 0);
+                if (sl.arch > 0xffu || sl.prims > 0xffu) {
+                    atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);   // does not fit the packed candidate
+                    sl.prims = 0;
+                }
             }
         }
         staged[k] = sl;
@@ -621,12 +675,18 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
             i32 self_id = 0;
             bool self_static = false;
             u32 self_prims = 0;
+            u32 self_info = 0;
             AABB box = AABB::invalid();
             if (valid) {
                 const u64 packed = ((const u64 *)t.columns[0])[row];
                 self_id = (i32)(u32)(packed >> 32);
                 self_static = bodyCol<u32>(S, b, PCResponseType, row) == kRespStatic;
                 self_prims = objs.primCounts[bodyCol<i32>(S, b, PCObjectID, row)];
+                self_info = bodySlotInfo(b.archetype, row, self_static);
+                if (b.archetype > 0xffu || self_prims > 0xffu) {
+                    atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+                    self_prims = 0;
+                }
                 const PAABB lb = bvh.leafAABBs[bodyCol<i32>(S, b, PCLeafID, row)];
                 box = AABB { { lb.pMin.x, lb.pMin.y, lb.pMin.z }, { lb.pMax.x, lb.pMax.y, lb.pMax.z } };
             }
@@ -668,7 +728,9 @@ __device__ void phaseFindCandidates(EngineState &S, const PhysicsState &P, const
                     const u32 checks = self_prims * sl.prims;
                     for (u32 c = 0; c < checks; c++) {
                         if (at < P.maxCandidatesPerWorld) {
-                            out[at] = Candidate { b.archetype, row, sl.arch, sl.row, c / sl.prims, c % sl.prims };
+                            out[at] = Candidate { b.archetype | (sl.arch << 8) | ((c / sl.prims) << 16) |
+                                                      ((c % sl.prims) << 24),
+                                                  row, sl.row, self_info | (sl.slotInfo << 16) };
                         }
                         at++;
                     }
@@ -1129,7 +1191,7 @@ __device__ __forceinline__ void writeContact(Contact &c, u32 ref_arch, i32 ref_r
     }
     c.numPoints = m.count;
     c.normal = PVec3 { m.normal.x, m.normal.y, m.normal.z };
-    for (int i = 0; i < 3; i++) c.lambdaN[i] = 0.f;
+    c.lambdaN = 0.f;
     c.level = 0;
 }
 
@@ -1163,6 +1225,7 @@ __device__ __forceinline__ ManifoldOut singlePoint(Vector3 p, Vector3 n, float d
 struct PairSetup {
     u32 aArch, bArch;
     i32 aRow, bRow;
+    u32 aInfo, bInfo;  // (world body slot << 1) | mutable, see Candidate::slots
     const PCollisionPrimitive *aPrim, *bPrim;
     Vector3 aPos, bPos;
     Quat aRot, bRot;
@@ -1170,14 +1233,16 @@ struct PairSetup {
     u32 test;          // 0 = rejected
 };
 
-__device__ __forceinline__ PairSetup setupPair(const EngineState &S, const PhysicsState &P,
-                                               const PObjectManager &objs, const Candidate &cand)
+template <bool REJECT>
+__device__ __forceinline__ PairSetup setupPairImpl(const EngineState &S, const PhysicsState &P,
+                                                   const PObjectManager &objs, const Candidate &cand)
 {
     PairSetup ps;
-    ps.aArch = cand.aArch; ps.bArch = cand.bArch;
+    ps.aArch = cand.archPrim & 0xffu; ps.bArch = (cand.archPrim >> 8) & 0xffu;
     ps.aRow = cand.aRow; ps.bRow = cand.bRow;
-    u32 a_prim_idx = objs.primOffsets[locCol<i32>(S, P, ps.aArch, ps.aRow, PCObjectID)] + cand.aPrim;
-    u32 b_prim_idx = objs.primOffsets[locCol<i32>(S, P, ps.bArch, ps.bRow, PCObjectID)] + cand.bPrim;
+    ps.aInfo = cand.slots & 0xffffu; ps.bInfo = cand.slots >> 16;
+    u32 a_prim_idx = objs.primOffsets[locCol<i32>(S, P, ps.aArch, ps.aRow, PCObjectID)] + ((cand.archPrim >> 16) & 0xffu);
+    u32 b_prim_idx = objs.primOffsets[locCol<i32>(S, P, ps.bArch, ps.bRow, PCObjectID)] + (cand.archPrim >> 24);
     ps.aPrim = &objs.prims[a_prim_idx];
     ps.bPrim = &objs.prims[b_prim_idx];
     u32 ta = ps.aPrim->type, tb = ps.bPrim->type;
@@ -1188,6 +1253,7 @@ __device__ __forceinline__ PairSetup setupPair(const EngineState &S, const Physi
         const PCollisionPrimitive *tp;
         tu = ps.aArch; ps.aArch = ps.bArch; ps.bArch = tu;
         ti = ps.aRow; ps.aRow = ps.bRow; ps.bRow = ti;
+        tu = ps.aInfo; ps.aInfo = ps.bInfo; ps.bInfo = tu;
         tp = ps.aPrim; ps.aPrim = ps.bPrim; ps.bPrim = tp;
         tu = a_prim_idx; a_prim_idx = b_prim_idx; b_prim_idx = tu;
         tu = ta; ta = tb; tb = tu;
@@ -1199,10 +1265,20 @@ __device__ __forceinline__ PairSetup setupPair(const EngineState &S, const Physi
     ps.aScale = locCol<Diag3x3>(S, P, ps.aArch, ps.aRow, PCScale);
     ps.bScale = locCol<Diag3x3>(S, P, ps.bArch, ps.bRow, PCScale);
 
-    AABB a_box = objs.primAABBs[a_prim_idx].applyTRS(ps.aPos, ps.aRot, ps.aScale);
-    AABB b_box = objs.primAABBs[b_prim_idx].applyTRS(ps.bPos, ps.bRot, ps.bScale);
-    ps.test = a_box.intersects(b_box) ? (ta | tb) : 0u;
+    if constexpr (REJECT) {
+        AABB a_box = objs.primAABBs[a_prim_idx].applyTRS(ps.aPos, ps.aRot, ps.aScale);
+        AABB b_box = objs.primAABBs[b_prim_idx].applyTRS(ps.bPos, ps.bRot, ps.bScale);
+        ps.test = a_box.intersects(b_box) ? (ta | tb) : 0u;
+    } else {
+        ps.test = ta | tb;
+    }
     return ps;
+}
+
+__device__ __forceinline__ PairSetup setupPair(const EngineState &S, const PhysicsState &P,
+                                               const PObjectManager &objs, const Candidate &cand)
+{
+    return setupPairImpl<true>(S, P, objs, cand);
 }
 
 // sphere (a) - hull (b): GJK closest point of the hull to the sphere centre, SAT
@@ -1391,32 +1467,46 @@ __device__ __forceinline__ T warpBroadcast(T v, int src)
     return out.t;
 }
 
+// Hull - hull pairs are worked on by GROUPS of kGroupLanes lanes, kNarrowGroups
+// pairs per warp at a time: a box has 6 faces and 8 vertices, so a whole warp on
+// one pair leaves most lanes idle in the face queries and all but one in the
+// clipping, and the pair's dependent load chains (primitive -> mesh -> vertex
+// arrays) are not overlapped with anything.  Four pairs in flight give four
+// independent chains per warp and keep 6 of 8 lanes busy in the face queries.
+constexpr int kGroupLanes = 8;
+constexpr int kNarrowGroups = 32 / kGroupLanes;
+
 // (separation, index) of the element the sequential scan would have kept.
 struct Winner {
     float sep;
     i32 idx;
 };
 
-__device__ __noinline__ Winner warpSequentialWinnerImpl(float sep, i32 idx, bool have)
+// Reduction over the lanes of one group (mask gm, xor distances stay inside the
+// aligned group).  Input per lane: its own candidate (sep, idx) chosen by the
+// same rule over the elements it looked at, or have = false.
+// Rule == the scalar loop "keep strictly greater, stop at the first positive":
+// lowest index among positives, else lowest index among maxima.
+__device__ __forceinline__ Winner groupSequentialWinner(unsigned gm, float sep, i32 idx, bool have)
 {
-    const u32 positives = __ballot_sync(0xffffffffu, have && sep > 0.f);
-    if (positives) {
-        // lowest index among positives; lanes hold disjoint ascending index sets,
-        // so compare indices explicitly
-        i32 cand = (have && sep > 0.f) ? idx : 0x7fffffff;
-        for (int o = 16; o >= 1; o >>= 1) {
-            i32 other = __shfl_xor_sync(0xffffffffu, cand, o);
+    const bool positive = have && sep > 0.f;
+    if (__any_sync(gm, positive)) {
+        i32 cand = positive ? idx : 0x7fffffff;
+#pragma unroll
+        for (int o = kGroupLanes / 2; o >= 1; o >>= 1) {
+            const i32 other = __shfl_xor_sync(gm, cand, o);
             if (other < cand) cand = other;
         }
-        const u32 owner = __ballot_sync(0xffffffffu, have && sep > 0.f && idx == cand);
+        const unsigned owner = __ballot_sync(gm, positive && idx == cand);
         const int src = __ffs(owner) - 1;
-        return Winner { __shfl_sync(0xffffffffu, sep, src), cand };
+        return Winner { __shfl_sync(gm, sep, src), cand };
     }
     float s = have ? sep : -FLT_MAX;
     i32 k = have ? idx : 0x7fffffff;
-    for (int o = 16; o >= 1; o >>= 1) {
-        float os = __shfl_xor_sync(0xffffffffu, s, o);
-        i32 ok = __shfl_xor_sync(0xffffffffu, k, o);
+#pragma unroll
+    for (int o = kGroupLanes / 2; o >= 1; o >>= 1) {
+        const float os = __shfl_xor_sync(gm, s, o);
+        const i32 ok = __shfl_xor_sync(gm, k, o);
         if (os > s || (os == s && ok < k)) {
             s = os;
             k = ok;
@@ -1425,26 +1515,39 @@ __device__ __noinline__ Winner warpSequentialWinnerImpl(float sep, i32 idx, bool
     return Winner { s, k };
 }
 
-__device__ __forceinline__ void warpSequentialWinner(float &sep, i32 &idx, bool have)
+// faces of one hull against the other hull's vertices: lane `sub` measures faces
+// sub, sub + 8, ... in ascending order with the scalar rule, then the group combines
+__device__ __forceinline__ Winner groupFaceQuery(unsigned gm, int sub, const PPlane *planes, u32 num_faces,
+                                                 const HullInWorld &other)
 {
-    const Winner w = warpSequentialWinnerImpl(sep, idx, have);
-    sep = w.sep;
-    idx = w.idx;
+    float best = -FLT_MAX;
+    i32 best_face = 0x7fffffff;
+    bool have = false;
+    for (u32 f = (u32)sub; f < num_faces; f += kGroupLanes) {
+        const float sep = hullSupportDistance(planes[f], other);
+        if (!have || sep > best) {
+            // first element, or strictly greater than what this lane kept so far
+            best = sep;
+            best_face = (i32)f;
+            have = true;
+            if (sep > 0.f) break;    // the scalar loop stops at the first positive
+        }
+    }
+    return groupSequentialWinner(gm, best, best_face, have);
 }
 
-// Executed by ALL lanes for the hull-hull candidate owned by lane `src`.
-// Returns (on every lane) whether a contact was produced; the contact itself
-// is valid on lane `src` only.
-__device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const int src, const int lane,
-                                    HullScratch &scratch, Contact &out)
+// Executed by the kGroupLanes lanes of one group for the hull - hull pair `ps`
+// (every lane holds the same copy); lane sub 0 writes the contact (if any) to
+// `out`.  Returns, on every lane of the group, whether a contact was made.
+__device__ bool hullHullGroup(EngineState &S, const PairSetup &ps, HullScratch &scratch, const unsigned gm,
+                              const int sub, Contact &out)
 {
-    const PairSetup ps = warpBroadcast(mine, src);
     const PHalfEdgeMesh &am = ps.aPrim->hull;
     const PHalfEdgeMesh &bm = ps.bPrim->hull;
     const u32 nva = am.numVertices, nvb = bm.numVertices, nfa = am.numFaces, nfb = bm.numFaces;
     if (nva > (u32)kMaxHullVerts || nvb > (u32)kMaxHullVerts ||
             nfa > (u32)kMaxHullFaces || nfb > (u32)kMaxHullFaces) {
-        if (lane == src) atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
+        if (sub == 0) atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
         return false;
     }
 
@@ -1455,23 +1558,24 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
         const Mat3x3 rot_a = Mat3x3::fromQuat(ps.aRot), rot_b = Mat3x3::fromQuat(ps.bRot);
         const Mat3x3 vm_a = rot_a * ps.aScale, vm_b = rot_b * ps.bScale;
         const Mat3x3 nm_a = rot_a * ps.aScale.inv(), nm_b = rot_b * ps.bScale.inv();
+        const Vector3 a_pos = ps.aPos, b_pos = ps.bPos;
 #pragma unroll 1
-        for (u32 i = lane; i < nva + nvb; i += 32) {
-            if (i < nva) verts_a[i] = vm_a * am.vertices[i] + ps.aPos;
-            else verts_b[i - nva] = vm_b * bm.vertices[i - nva] + ps.bPos;
+        for (u32 i = (u32)sub; i < nva + nvb; i += kGroupLanes) {
+            if (i < nva) verts_a[i] = vm_a * am.vertices[i] + a_pos;
+            else verts_b[i - nva] = vm_b * bm.vertices[i - nva] + b_pos;
         }
 #pragma unroll 1
-        for (u32 i = lane; i < nfa + nfb; i += 32) {
+        for (u32 i = (u32)sub; i < nfa + nfb; i += kGroupLanes) {
             const bool is_a = i < nfa;
             const PPlane local = is_a ? am.facePlanes[i] : bm.facePlanes[i - nfa];
             const Mat3x3 &vm = is_a ? vm_a : vm_b;
             const Mat3x3 &nm = is_a ? nm_a : nm_b;
-            const Vector3 on_plane = vm * (local.normal * local.d) + (is_a ? ps.aPos : ps.bPos);
+            const Vector3 on_plane = vm * (local.normal * local.d) + (is_a ? a_pos : b_pos);
             const Vector3 n = (nm * local.normal).normalize();
             (is_a ? planes_a[i] : planes_b[i - nfa]) = PPlane { n, dot(n, on_plane) };
         }
     }
-    __syncwarp();
+    __syncwarp(gm);
     // centres: vertex sums in index order (float addition is not associative)
     Vector3 center_a = Vector3::zero();
 #pragma unroll 1
@@ -1481,23 +1585,21 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
     HullInWorld a { &am, verts_a, planes_a, nva, nfa, center_a };
     HullInWorld b { &bm, verts_b, planes_b, nvb, nfb, Vector3::zero() };
 
-    // -- face queries: lane f measures face f (A's faces vs B, then B's vs A)
-    float sep_a = -FLT_MAX, sep_b = -FLT_MAX;
-    i32 face_a = lane, face_b = lane;
-    if ((u32)lane < nfa) sep_a = hullSupportDistance(planes_a[lane], b);
-    warpSequentialWinner(sep_a, face_a, (u32)lane < nfa);
-    if (sep_a > 0.0f) return false;
-    if ((u32)lane < nfb) sep_b = hullSupportDistance(planes_b[lane], a);
-    warpSequentialWinner(sep_b, face_b, (u32)lane < nfb);
-    if (sep_b > 0.0f) return false;
+    // -- face queries (A's faces vs B, then B's vs A)
+    const Winner fa = groupFaceQuery(gm, sub, planes_a, nfa, b);
+    if (fa.sep > 0.0f) return false;
+    const Winner fb = groupFaceQuery(gm, sub, planes_b, nfb, a);
+    if (fb.sep > 0.0f) return false;
+    const float sep_a = fa.sep, sep_b = fb.sep;
+    const i32 face_a = fa.idx, face_b = fb.idx;
 
-    // -- edge query: pair p = ia * eb + ib, lanes take p = lane, lane + 32, ...
+    // -- edge query: pair p = ia * eb + ib, lanes take p = sub, sub + 8, ...
     const u32 ea = am.numHalfEdges / 2, eb = bm.numHalfEdges / 2;
     float e_sep = -FLT_MAX;
     i32 e_pair = 0x7fffffff;
     Vector3 e_normal = Vector3::zero();
 #pragma unroll 1
-    for (u32 p = lane; p < ea * eb; p += 32) {
+    for (u32 p = (u32)sub; p < ea * eb; p += kGroupLanes) {
         const u32 ha = (p / eb) * 2, hb = (p % eb) * 2;
         const PHalfEdge a0 = am.halfEdges[ha];
         const PHalfEdge a1 = am.halfEdges[ha ^ 1u];
@@ -1529,11 +1631,16 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
     {
         const float my_sep = e_sep;
         const i32 my_pair = e_pair;
-        warpSequentialWinner(e_sep, e_pair, my_pair != 0x7fffffff);
-        const u32 owner = __ballot_sync(0xffffffffu, my_pair == e_pair && my_pair != 0x7fffffff &&
-                                                     my_sep == e_sep);
+        const Winner ew = groupSequentialWinner(gm, e_sep, e_pair, my_pair != 0x7fffffff);
+        e_sep = ew.sep;
+        e_pair = ew.idx;
+        const unsigned owner = __ballot_sync(gm, my_pair == e_pair && my_pair != 0x7fffffff &&
+                                                 my_sep == e_sep);
         if (owner) {
-            e_normal = warpBroadcast(e_normal, __ffs(owner) - 1);
+            const int src = __ffs(owner) - 1;
+            e_normal.x = __shfl_sync(gm, e_normal.x, src);
+            e_normal.y = __shfl_sync(gm, e_normal.y, src);
+            e_normal.z = __shfl_sync(gm, e_normal.z, src);
         } else {
             // nothing beat the initial -FLT_MAX: the scalar scan keeps its defaults
             e_sep = -FLT_MAX;
@@ -1543,9 +1650,9 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
     }
     if (e_sep > 0.0f) return false;
 
-    // -- contact generation on the owning lane (data already in shared memory)
+    // -- contact generation on the group's first lane (data already in shared memory)
     bool made = false;
-    if (lane == src) {
+    if (sub == 0) {
         const bool face_contact_a = sep_a > e_sep;
         const bool face_contact_b = sep_b > e_sep;
         if (face_contact_a || face_contact_b) {
@@ -1558,8 +1665,13 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
             ManifoldOut m = faceFaceManifold(ref_plane, ref_face, inc_face, ref, inc,
                                              scratch.clipA, scratch.clipB);
             if (m.count > 0) {
-                if (a_is_ref) writeContact(out, ps.aArch, ps.aRow, ps.bArch, ps.bRow, m);
-                else writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, m);
+                if (a_is_ref) {
+                    writeContact(out, ps.aArch, ps.aRow, ps.bArch, ps.bRow, m);
+                    out.refInfo = ps.aInfo; out.altInfo = ps.bInfo;
+                } else {
+                    writeContact(out, ps.bArch, ps.bRow, ps.aArch, ps.aRow, m);
+                    out.refInfo = ps.bInfo; out.altInfo = ps.aInfo;
+                }
                 made = true;
             }
         } else {
@@ -1571,120 +1683,180 @@ __device__ bool hullHullCooperative(EngineState &S, const PairSetup &mine, const
                 verts_a[he_a.rootVertex], verts_a[am.halfEdges[he_a.next].rootVertex],
                 verts_b[he_b.rootVertex], verts_b[bm.halfEdges[he_b.next].rootVertex]);
             writeContact(out, ps.aArch, ps.aRow, ps.bArch, ps.bRow, singlePoint(p, e_normal, -e_sep));
+            out.refInfo = ps.aInfo; out.altInfo = ps.bInfo;
             made = true;
         }
     }
-    made = __shfl_sync(0xffffffffu, made ? 1 : 0, src) != 0;
-    __syncwarp();
-    return made;
+    return __shfl_sync(gm, made ? 1 : 0, (__ffs(gm) - 1)) != 0;
 }
 
-// A body takes part in contact ordering unless writing it back is a no-op:
-// static (inverse mass / inertia forced to 0, so x is unchanged) AND its
-// rotation is a bitwise fixpoint of normalize() (so q is unchanged).
-__device__ __forceinline__ bool bodyIsMutable(const EngineState &S, const PhysicsState &P, u32 arch, i32 row)
-{
-    if (locCol<u32>(S, P, arch, row, PCResponseType) != kRespStatic) return true;
-    const Quat q = locCol<Quat>(S, P, arch, row, PCRotation);
-    const Quat n = q.normalize();
-    return !(n.w == q.w && n.x == q.x && n.y == q.y && n.z == q.z);
-}
-
-// index of a body inside its world's body list (archetypes ascending, rows in order)
-__device__ __forceinline__ i32 worldBodySlot(const EngineState &S, const PhysicsState &P, i32 w, u32 arch, i32 row)
-{
-    i32 base = 0;
-    for (u32 i = 0; i < P.numBodyArchetypes; i++) {
-        const TableDesc &t = S.tables[P.bodies[i].archetype];
-        if (P.bodies[i].archetype == arch) return base + (row - t.worldOffsets[w]);
-        base += t.worldCounts[w];
-    }
-    return -1;
-}
-
-// one warp per world: candidates in order, contacts compacted in order, then
-// the dependency level of every contact (see Contact::level)
-
-struct LevelScratch {
-    i32 lastLevel[kPhysWarps][kMaxLevelBodies];
-    i32 pairInfo[kPhysWarps][32][2];   // body slot * 2 + mutable, per side
-    i32 levelOut[kPhysWarps][32];
-    HullScratch hulls[kPhysWarps];
-};
+// ---- narrowphase, dense over the candidates of ALL worlds ------------------------------------
+// The contact of candidate i of world w lives in slot (w, i), so nothing here
+// needs per-world ordering:
+//   physNarrowSimpleKernel  one THREAD per candidate (a block flattens the candidate
+//       lists of kNarrowWorldsPerBlock worlds, so lanes stay busy whatever the
+//       per-world counts are): pair setup + primitive-box reject; sphere / plane
+//       pair types are finished on the spot, hull - hull survivors are queued;
+//   physNarrowHullKernel    one 8-lane GROUP per queued hull - hull pair, groups
+//       stride over the queue (4 pairs in flight per warp, every lane busy);
+//   orderContacts (prologue of the position solve) lists each world's hits in
+//       candidate order and assigns the dependency levels.
+constexpr int kNarrowWorldsPerBlock = 8;
+constexpr int kNarrowSimpleThreads = 128;
 
 template <bool SPHERE_HULL>
-__device__ void phaseNarrowphase(EngineState &S, const PhysicsState &P, const i32 w, const int lane,
-                                 const int warp, LevelScratch &scratch)
+__global__ void __launch_bounds__(kNarrowSimpleThreads, 6)
+physNarrowSimpleKernel(EngineState *Sp)
 {
-    i32 (&last_level)[kPhysWarps][kMaxLevelBodies] = scratch.lastLevel;
-    i32 (&pair_info)[kPhysWarps][32][2] = scratch.pairInfo;
-    i32 (&level_out)[kPhysWarps][32] = scratch.levelOut;
-    for (int i = lane; i < kMaxLevelBodies; i += 32) last_level[warp][i] = 0;
-    __syncwarp();
-
-    const PObjectManager &objs = worldObjects(S, P, w);
-    const Candidate *cands = P.candidates + (size_t)w * P.maxCandidatesPerWorld;
-    Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
-    const i32 n = P.candCounts[w];
-    i32 running = 0;
-    i32 max_level = 0;
-    i32 seq_level = 0;      // fallback when a world has more bodies than the scan tracks
-
-    for (i32 base = 0; base < n; base += 32) {
-        const i32 i = base + lane;
-        Contact c;
-        bool hit = false;
-        PairSetup ps;
-        ps.test = 0;
-        if (i < n) ps = setupPair(S, P, objs, cands[i]);
-        if (ps.test != 0 && ps.test != 2) hit = narrowphaseSimple<SPHERE_HULL>(S, ps, c);
-        u32 hull_pairs = __ballot_sync(0xffffffffu, ps.test == 2);
-        while (hull_pairs) {
-            const int src = __ffs(hull_pairs) - 1;
-            hull_pairs &= hull_pairs - 1;
-            const bool made = hullHullCooperative(S, ps, src, lane, scratch.hulls[warp], c);
-            if (lane == src) hit = made;
+    EngineState &S = *Sp;
+    const PhysicsState &P = *S.physics;
+    __shared__ i32 first[kNarrowWorldsPerBlock + 1];
+    const i32 w0 = (i32)blockIdx.x * kNarrowWorldsPerBlock;
+    if (threadIdx.x == 0) {
+        i32 acc = 0;
+        for (int k = 0; k < kNarrowWorldsPerBlock; k++) {
+            first[k] = acc;
+            if (w0 + k < (i32)S.numWorlds) acc += P.candCounts[w0 + k];
         }
-        const u32 hits = __ballot_sync(0xffffffffu, hit);
-        const int my_rank = __popc(hits & ((1u << lane) - 1u));
-        const int num_hits = __popc(hits);
+        first[kNarrowWorldsPerBlock] = acc;
+    }
+    __syncthreads();
+    const i32 total = first[kNarrowWorldsPerBlock];
+    const int lane = threadIdx.x & 31;
+
+    for (i32 j0 = 0; j0 < total; j0 += kNarrowSimpleThreads) {
+        const i32 j = j0 + (i32)threadIdx.x;
+        const bool have = j < total;
+        i32 w = w0, i = 0;
+        u32 test = 0;
+        if (have) {
+            int k = 0;
+            while (j >= first[k + 1]) k++;
+            w = w0 + k;
+            i = j - first[k];
+            const size_t slot = (size_t)w * P.maxCandidatesPerWorld + i;
+            const PObjectManager &objs = worldObjects(S, P, w);
+            const PairSetup ps = setupPair(S, P, objs, P.candidates[slot]);
+            test = ps.test;
+            bool hit = false;
+            if (test != 0 && test != 2) {
+                Contact c;
+                hit = narrowphaseSimple<SPHERE_HULL>(S, ps, c);
+                if (hit) {
+                    // single-point and hull - plane contacts store (ref, alt) = (b, a)
+                    c.refInfo = ps.bInfo;
+                    c.altInfo = ps.aInfo;
+                    P.contacts[slot] = c;
+                }
+            }
+            P.candHit[slot] = hit ? 1 : 0;
+        }
+        // queue the hull - hull survivors (one atomic per warp)
+        const unsigned hh = __ballot_sync(0xffffffffu, have && test == 2);
+        if (hh) {
+            const int leader = __ffs(hh) - 1;
+            i32 base = 0;
+            if (lane == leader) base = atomicAdd(P.hullQueueCount, __popc(hh));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (have && test == 2) {
+                P.hullQueue[base + __popc(hh & ((1u << lane) - 1u))] = HullQueueEntry { w, i };
+            }
+        }
+    }
+}
+
+constexpr int kNarrowHullThreads = 64;
+
+__global__ void __launch_bounds__(kNarrowHullThreads, 8)
+physNarrowHullKernel(EngineState *Sp)
+{
+    EngineState &S = *Sp;
+    const PhysicsState &P = *S.physics;
+    __shared__ HullScratch scratch[kNarrowHullThreads / kGroupLanes];
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % kGroupLanes;
+    const int group_in_warp = lane / kGroupLanes;
+    const int group_in_block = threadIdx.x / kGroupLanes;
+    const unsigned gm = ((1u << kGroupLanes) - 1u) << (group_in_warp * kGroupLanes);
+    const i32 count = *P.hullQueueCount;
+    const i32 groups_per_block = kNarrowHullThreads / kGroupLanes;
+    for (i32 e = (i32)blockIdx.x * groups_per_block + group_in_block; e < count;
+         e += (i32)gridDim.x * groups_per_block) {
+        const HullQueueEntry ent = P.hullQueue[e];
+        const size_t slot = (size_t)ent.world * P.maxCandidatesPerWorld + ent.cand;
+        const PObjectManager &objs = worldObjects(S, P, ent.world);
+        const PairSetup ps = setupPairImpl<false>(S, P, objs, P.candidates[slot]);
+        const bool made = hullHullGroup(S, ps, scratch[group_in_block], gm, sub, P.contacts[slot]);
+        if (sub == 0 && made) P.candHit[slot] = 1;
+        __syncwarp(gm);
+    }
+}
+
+// Prologue of the position solve, run by the LPW lanes that own world w: list
+// the world's contact slots in candidate order and give every contact its
+// dependency level (see Contact::level) -- a sequential scan by the group's
+// first lane over flags / body infos its lanes fetched in parallel.
+template <int LPW>
+__device__ __forceinline__ void orderContacts(EngineState &S, const PhysicsState &P, const i32 w, const bool valid,
+                                              const int lane, i32 *last_level /* [kMaxLevelBodies] of this world */)
+{
+    constexpr unsigned kGroupMask = LPW == 32 ? 0xffffffffu : ((1u << (LPW & 31)) - 1u);
+    const int sub = lane & (LPW - 1);
+    const int group_shift = (lane / LPW) * LPW;
+    const unsigned gm = kGroupMask << group_shift;
+
+    for (int i = sub; i < kMaxLevelBodies; i += LPW) last_level[i] = 0;
+    __syncwarp(gm);
+
+    const i32 n = valid ? P.candCounts[w] : 0;
+    const size_t base_slot = (size_t)w * P.maxCandidatesPerWorld;
+    Contact *contacts = P.contacts + base_slot;
+    i32 *order = P.contactOrder + (size_t)w * P.maxContactsPerWorld;
+    i32 running = 0, max_level = 0, seq_level = 0;
+
+    for (i32 base = 0; base < n; base += LPW) {
+        const i32 i = base + sub;
+        const bool hit = i < n && P.candHit[base_slot + i] != 0;
+        u32 a = 0, b = 0;
         if (hit) {
-            const i32 s1 = worldBodySlot(S, P, w, c.refArch, c.refRow);
-            const i32 s2 = worldBodySlot(S, P, w, c.altArch, c.altRow);
-            pair_info[warp][my_rank][0] = s1 * 2 + (bodyIsMutable(S, P, c.refArch, c.refRow) ? 1 : 0);
-            pair_info[warp][my_rank][1] = s2 * 2 + (bodyIsMutable(S, P, c.altArch, c.altRow) ? 1 : 0);
+            a = contacts[i].refInfo;
+            b = contacts[i].altInfo;
         }
-        __syncwarp();
-        if (lane == 0) {
-            for (int k = 0; k < num_hits; k++) {
-                const i32 a = pair_info[warp][k][0], b = pair_info[warp][k][1];
-                const i32 sa = a >> 1, sb = b >> 1;
-                i32 lvl;
-                if (sa < 0 || sb < 0 || sa >= kMaxLevelBodies || sb >= kMaxLevelBodies) {
+        const unsigned hits = (__ballot_sync(gm, hit) >> group_shift) & kGroupMask;
+        i32 my_level = 0;
+        unsigned todo = hits;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const u32 sa_info = __shfl_sync(gm, a, group_shift + src);
+            const u32 sb_info = __shfl_sync(gm, b, group_shift + src);
+            i32 lvl = 0;
+            if (sub == 0) {
+                const u32 sa = sa_info >> 1, sb = sb_info >> 1;
+                if (sa >= (u32)kMaxLevelBodies || sb >= (u32)kMaxLevelBodies) {
                     lvl = max_level + 1;          // unknown body: strictly after everything so far
                     seq_level = lvl;
                 } else {
                     i32 dep = seq_level;
-                    if (a & 1) dep = max(dep, last_level[warp][sa]);
-                    if (b & 1) dep = max(dep, last_level[warp][sb]);
+                    if (sa_info & 1u) dep = max(dep, last_level[sa]);
+                    if (sb_info & 1u) dep = max(dep, last_level[sb]);
                     lvl = dep + 1;
-                    if (a & 1) last_level[warp][sa] = lvl;
-                    if (b & 1) last_level[warp][sb] = lvl;
+                    if (sa_info & 1u) last_level[sa] = lvl;
+                    if (sb_info & 1u) last_level[sb] = lvl;
                 }
                 if (lvl > max_level) max_level = lvl;
-                level_out[warp][k] = lvl;
             }
+            lvl = __shfl_sync(gm, lvl, group_shift);
+            if (sub == src) my_level = lvl;
         }
-        __syncwarp();
         if (hit) {
-            const i32 at = running + my_rank;
-            c.level = level_out[warp][my_rank];
-            if (at < P.maxContactsPerWorld) contacts[at] = c;
+            const i32 at = running + __popc(hits & ((1u << sub) - 1u));
+            contacts[i].level = my_level;
+            if (at < P.maxContactsPerWorld) order[at] = i;
         }
-        running += num_hits;
-        __syncwarp();
+        running += __popc(hits);
     }
-    if (lane == 0) {
+    if (valid && sub == 0) {
         if (running > P.maxContactsPerWorld) {
             atomicOr(&S.errorFlags, (u32)ErrPhysicsOverflow);
             running = P.maxContactsPerWorld;
@@ -1692,6 +1864,7 @@ __device__ void phaseNarrowphase(EngineState &S, const PhysicsState &P, const i3
         P.contactCounts[w] = running;
         P.contactMaxLevel[w] = max_level;
     }
+    __syncwarp(gm);
 }
 
 // =============================================================================================
@@ -1793,7 +1966,7 @@ __device__ __forceinline__ BodyPair bodyPair(const EngineState &S, const Physics
 __device__ void solveContactPosition(EngineState &S, const PhysicsState &P, const PObjectManager &objs,
                                      Contact &c)
 {
-    for (int i = 0; i < 3; i++) c.lambdaN[i] = 0.f;
+    c.lambdaN = 0.f;
 
     Vector3 &x1_ref = locCol<Vector3>(S, P, c.refArch, c.refRow, PCPosition);
     Vector3 &x2_ref = locCol<Vector3>(S, P, c.altArch, c.altRow, PCPosition);
@@ -1823,7 +1996,7 @@ __device__ void solveContactPosition(EngineState &S, const PhysicsState &P, cons
     const float d = dot(p1 - p2, n);
     if (d > 0) {
         const float lambda_n = positionalCorrection(x1, x2, q1, q2, r1, r2, bp, n, d, 0);
-        c.lambdaN[0] = lambda_n;
+        c.lambdaN = lambda_n;
 
         const Vector3 p1_hat = prev1.q.rotateVec(r1) + prev1.x;
         const Vector3 p2_hat = prev2.q.rotateVec(r2) + prev2.x;
@@ -1955,8 +2128,8 @@ __device__ void solveJoint(EngineState &S, const PhysicsState &P, const PObjectM
 constexpr int kSolverLanes = MB2_SOLVER_LPW;
 
 template <int LPW, typename Fn>
-__device__ __forceinline__ void sweepContactLevels(const Contact *contacts, const i32 n, const i32 levels,
-                                                   const int lane, Fn &&solve)
+__device__ __forceinline__ void sweepContactLevels(const Contact *contacts, const i32 *order, const i32 n,
+                                                   const i32 levels, const int lane, Fn &&solve)
 {
     constexpr int kPerLane = 32 / LPW;
     constexpr unsigned kGroupMask = LPW == 32 ? 0xffffffffu : ((1u << (LPW & 31)) - 1u);
@@ -1975,7 +2148,7 @@ __device__ __forceinline__ void sweepContactLevels(const Contact *contacts, cons
 #pragma unroll
         for (int r = 0; r < kPerLane; r++) {
             const i32 i = base + r * LPW + sub;
-            lv[r] = i < n ? contacts[i].level : 0;
+            lv[r] = i < n ? contacts[order[i]].level : 0;
         }
         for (i32 lvl = 1; lvl <= levels_max; lvl++) {
             unsigned members = 0;
@@ -1986,7 +2159,9 @@ __device__ __forceinline__ void sweepContactLevels(const Contact *contacts, cons
             }
             const int count = __popc(members);
             for (int k = sub; k < count; k += LPW) {
-                solve(base + (i32)__fns(members, 0, k + 1));
+                // member bit m = r * LPW + lane-in-group: fetch that lane's slot[r]
+                const int m = (int)__fns(members, 0, k + 1);
+                solve(order[base + m]);
             }
             __syncwarp();
         }
@@ -1999,10 +2174,11 @@ __device__ void phaseSolvePositions(EngineState &S, const PhysicsState &P, const
 {
     const PObjectManager &objs = worldObjects(S, P, w);
 
-    Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
+    Contact *contacts = P.contacts + (size_t)w * P.maxCandidatesPerWorld;
+    const i32 *order = P.contactOrder + (size_t)w * P.maxContactsPerWorld;
     const i32 n = valid ? P.contactCounts[w] : 0;
     const i32 levels = valid ? P.contactMaxLevel[w] : 0;
-    sweepContactLevels<kSolverLanes>(contacts, n, levels, lane, [&](i32 i) {
+    sweepContactLevels<kSolverLanes>(contacts, order, n, levels, lane, [&](i32 i) {
         solveContactPosition(S, P, objs, contacts[i]);
     });
 
@@ -2089,7 +2265,7 @@ __device__ void solveContactVelocity(EngineState &S, const PhysicsState &P, cons
                   c.points[i][3], n, &r1, &r2);
         const Vector3 r1_world = q1.rotateVec(r1);
         const Vector3 r2_world = q2.rotateVec(r2);
-        const float lambda = c.lambdaN[0] * (c.points[i][3] / pen_sum);
+        const float lambda = c.lambdaN * (c.points[i][3] / pen_sum);
 
         const Vector3 v = relativeVelocity(v1, v2, o1, o2, r1_world, r2_world);
         const float vn = dot(n, v);
@@ -2125,10 +2301,11 @@ __device__ void phaseSolveVelocities(EngineState &S, const PhysicsState &P, cons
 {
     const PObjectManager &objs = worldObjects(S, P, w);
     const PhysicsWorldParams &params = worldParams(S, P, w);
-    const Contact *contacts = P.contacts + (size_t)w * P.maxContactsPerWorld;
+    const Contact *contacts = P.contacts + (size_t)w * P.maxCandidatesPerWorld;
+    const i32 *order = P.contactOrder + (size_t)w * P.maxContactsPerWorld;
     const i32 n = valid ? P.contactCounts[w] : 0;
     const i32 levels = valid ? P.contactMaxLevel[w] : 0;
-    sweepContactLevels<kSolverLanes>(contacts, n, levels, lane, [&](i32 i) {
+    sweepContactLevels<kSolverLanes>(contacts, order, n, levels, lane, [&](i32 i) {
         solveContactVelocity(S, P, objs, contacts[i], params.h, params.restitutionThreshold);
     });
 }
@@ -2209,7 +2386,7 @@ __device__ __forceinline__ void forEachWorldBody(const EngineState &S, const Phy
 #ifndef MB2_NARROW_MINB
 #define MB2_NARROW_MINB 8
 #endif
-constexpr int physMinBlocks(u32 op) { return (op == 6u || op == 10u) /* narrowphase */ ? MB2_NARROW_MINB : 8; }
+constexpr int physMinBlocks(u32) { return 8; }
 
 template <u32 OP>
 __global__ void __launch_bounds__(32 * kPhysWarps, physMinBlocks(OP))
@@ -2226,20 +2403,21 @@ physWorldKernel(EngineState *Sp)
         const i32 my_w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) / kSolverLanes);
         const bool valid = my_w < (i32)S.numWorlds;
         const i32 w = valid ? my_w : (i32)S.numWorlds - 1;
-        if constexpr (OP == PhaseSolvePositions) phaseSolvePositions(S, P, w, valid, lane);
-        else phaseSolveVelocities(S, P, w, valid, lane);
+        if constexpr (OP == PhaseSolvePositions) {
+            // the hull queue of this substep has been consumed: empty it for the next one
+            if (blockIdx.x == 0 && threadIdx.x == 0) *P.hullQueueCount = 0;
+            __shared__ i32 last_level[32 * kPhysWarps / kSolverLanes][kMaxLevelBodies];
+            orderContacts<kSolverLanes>(S, P, w, valid, lane, last_level[threadIdx.x / kSolverLanes]);
+            phaseSolvePositions(S, P, w, valid, lane);
+        } else {
+            phaseSolveVelocities(S, P, w, valid, lane);
+        }
     } else {
         const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
         if (w >= (i32)S.numWorlds) return;
         if constexpr (OP == PhaseFindCandidates) {
             __shared__ CandidateScratch cand_scratch;
             phaseFindCandidates(S, P, w, lane, warp, cand_scratch);
-        } else if constexpr (OP == PhaseNarrowphase) {
-            __shared__ LevelScratch scratch;
-            phaseNarrowphase<false>(S, P, w, lane, warp, scratch);
-        } else if constexpr (OP == PhaseNarrowphaseSpheres) {
-            __shared__ LevelScratch scratch;
-            phaseNarrowphase<true>(S, P, w, lane, warp, scratch);
         }
     }
 }
@@ -2313,7 +2491,11 @@ bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *, std::stri
     };
     if (!alloc((void **)&P.candidates, sizeof(Candidate) * W * P.maxCandidatesPerWorld) ||
         !alloc((void **)&P.candCounts, sizeof(i32) * W) ||
-        !alloc((void **)&P.contacts, sizeof(Contact) * W * P.maxContactsPerWorld) ||
+        !alloc((void **)&P.contacts, sizeof(Contact) * W * P.maxCandidatesPerWorld) ||
+        !alloc((void **)&P.candHit, sizeof(i32) * W * P.maxCandidatesPerWorld) ||
+        !alloc((void **)&P.contactOrder, sizeof(i32) * W * P.maxContactsPerWorld) ||
+        !alloc((void **)&P.hullQueue, sizeof(HullQueueEntry) * W * P.maxCandidatesPerWorld) ||
+        !alloc((void **)&P.hullQueueCount, sizeof(i32) * 4) ||
         !alloc((void **)&P.contactCounts, sizeof(i32) * W) ||
         !alloc((void **)&P.contactMaxLevel, sizeof(i32) * W)) {
         *err = "physics buffers allocation failed";
@@ -2384,8 +2566,12 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
             physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
             break;
         case NodePhysNarrowphase:
-            if (ph->spheres) physWorldKernel<PhaseNarrowphaseSpheres><<<wgrid, wblock, 0, s>>>(d);
-            else physWorldKernel<PhaseNarrowphase><<<wgrid, wblock, 0, s>>>(d);
+            {
+                const unsigned sgrid_n = (W + kNarrowWorldsPerBlock - 1) / kNarrowWorldsPerBlock;
+                if (ph->spheres) physNarrowSimpleKernel<true><<<sgrid_n, kNarrowSimpleThreads, 0, s>>>(d);
+                else physNarrowSimpleKernel<false><<<sgrid_n, kNarrowSimpleThreads, 0, s>>>(d);
+                physNarrowHullKernel<<<(unsigned)ex->numSMs * 8u, kNarrowHullThreads, 0, s>>>(d);
+            }
             break;
         case NodePhysSolvePositions:
             physWorldKernel<PhaseSolvePositions><<<sgrid, wblock, 0, s>>>(d);

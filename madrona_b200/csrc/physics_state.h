@@ -16,6 +16,7 @@ namespace mb2 {
 
 struct PVec3 { float x, y, z; };
 struct PQuat { float w, x, y, z; };
+struct alignas(16) PVec4 { float x, y, z, w; };
 struct PAABB { PVec3 pMin, pMax; };
 
 // == broadphase::BVH::Node (include/madrona/broadphase.hpp:62-78): 4-wide node,
@@ -52,6 +53,13 @@ struct WorldBVH {
     // the survivors, so a query's result list is this list filtered by box
     // overlap -- which lets the candidate search run as a uniform loop.
     i32 *traversalOrder;
+    // The same list with the boxes inlined, 32 B per entry: the leaf's slot box in
+    // its parent node (grow-only between rebuilds) + the leaf index --
+    //   {min.x, min.y, min.z, max.x}, {max.y, max.z, leaf (int bits), 0}
+    // kept current by rebuild / refit, read by the candidate search and by
+    // BVH::traceRay as a flat, coalesced array (no node pointer chasing).
+    PVec4 *orderedBoxes;
+    i32 *leafOrderPos;        // leaf -> position in the list
     i32 numNodes;
     i32 numAllocatedNodes;
     i32 numLeaves;
@@ -73,12 +81,24 @@ struct PhysicsWorldParams {
     u32 jointArchetypeID;
 };
 
-// == phys::CandidateCollision (physics.hpp:52-57)
+// Role of phys::CandidateCollision (physics.hpp:52-57: two Locs + two primitive
+// indices, 24 B), packed to 16 B and extended with what the narrowphase would
+// otherwise look up again per contact:
+//   archPrim = aArch | bArch << 8 | aPrim << 16 | bPrim << 24
+//   slots    = aSlot | aMutable << 15 | ... same for b in the high half, i.e.
+//              ((slot << 1) | mutable) per side with slot = index of the body in
+//              its world's body list (0x7fff: unknown) and mutable = "writing the
+//              body back can change it" (see rotationIsNormalizeFixpoint).
 struct Candidate {
-    u32 aArch; i32 aRow;
-    u32 bArch; i32 bRow;
-    u32 aPrim;
-    u32 bPrim;
+    u32 archPrim;
+    i32 aRow;
+    i32 bRow;
+    u32 slots;
+};
+
+struct HullQueueEntry {
+    i32 world;
+    i32 cand;
 };
 
 // == phys::ContactConstraint (physics.hpp:59-65) + xpbd::XPBDContactState
@@ -88,7 +108,9 @@ struct Contact {
     float points[4][4];       // xyz + penetration depth
     i32 numPoints;
     PVec3 normal;
-    float lambdaN[3];         // only [0] is ever read (xpbd.cpp:1028)
+    float lambdaN;            // XPBDContactState::lambdaN[0], the only one ever read (xpbd.cpp:1028)
+    u32 refInfo;              // (world body slot << 1) | mutable of ref / alt (Candidate::slots)
+    u32 altInfo;
     // Dependency level inside the world's contact list: contacts of one level
     // touch disjoint (mutable) bodies and every earlier contact they could
     // depend on has a lower level, so solving level by level in parallel is
@@ -137,10 +159,19 @@ struct PhysicsState {
     Candidate *candidates;       // [numWorlds][maxCandidatesPerWorld]
     i32 *candCounts;             // [numWorlds]
     i32 maxCandidatesPerWorld;
-    Contact *contacts;           // [numWorlds][maxContactsPerWorld]
+    // A candidate's contact lives in the slot of the same index (so the dense
+    // narrowphase kernels need no per-world ordering); candHit marks the slots
+    // that hold a contact this substep, contactOrder lists them in candidate
+    // order (== the CPU backend's contact order) for the solvers.
+    Contact *contacts;           // [numWorlds][maxCandidatesPerWorld]
+    i32 *candHit;                // [numWorlds][maxCandidatesPerWorld]
+    i32 *contactOrder;           // [numWorlds][maxContactsPerWorld] -> slot
     i32 *contactCounts;
     i32 *contactMaxLevel;        // [numWorlds]
     i32 maxContactsPerWorld;
+    // hull - hull candidates that passed the primitive-box test, any order
+    HullQueueEntry *hullQueue;   // [numWorlds * maxCandidatesPerWorld]
+    i32 *hullQueueCount;
 };
 
 }

@@ -314,6 +314,8 @@ inline void init(Context &ctx,
     bvh.leafParents = (uint32_t *)carve(4 * max_leaves);
     bvh.sortedLeaves = (int32_t *)carve(4 * max_leaves);
     bvh.traversalOrder = (int32_t *)carve(4 * max_leaves);
+    bvh.orderedBoxes = (mb2::PVec4 *)carve(sizeof(mb2::PVec4) * 2 * max_leaves);
+    bvh.leafOrderPos = (int32_t *)carve(4 * max_leaves);
     bvh.numTraversal = 0;
     bvh.numNodes = 0;
     bvh.numAllocatedNodes = (int32_t)num_nodes;
@@ -541,71 +543,47 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
 {
     math::Diag3x3 inv_d = math::Diag3x3::fromVec(d).inv();
 
-    // Two-phase traversal: every lane first walks the tree up to its next
-    // entered leaf, then the lanes that called together run the (expensive)
-    // leaf test together; the warp votes keep the compiler from folding the
-    // two phases back into one divergent loop.
-    //
-    // Walking is latency bound, so a popped node is read once, whole (28
-    // independent loads), and its four slab tests run side by side.  The
-    // reference tests child i against the t_max current at that moment
-    // (src/physics/broadphase.cpp:658-724 + math.inl:1670-1696):
+    // The reference walks the 4-wide tree with a stack (src/physics/
+    // broadphase.cpp:658-724), testing child i of a popped node against the
+    // t_max current at that moment:
     //   max(mins.x, mins.y, mins.z, 0) <= min(maxes.x, maxes.y, maxes.z, t_max)
-    // with NaN-skipping fminf / fmaxf.  t_max is never NaN, so the right side
-    // equals fminf(min(maxes...), t_max): the box part (entry, exit) is
-    // evaluated at pop time, the comparison when the child's turn comes -- same
-    // decisions, same visit order (pop node, children 0..3 in order).
+    // (math.inl:1670-1696, NaN-skipping fminf / fmaxf).  A leaf is entered iff
+    // its own slot box passes that test when its turn comes: every ancestor box
+    // contains it (the slab expressions are monotonic in the box bounds and
+    // t_max only shrinks), and leaves are met in the tree's fixed report order.
+    // So the walk is a linear scan over WorldBVH::orderedBoxes -- same leaves,
+    // same order, same floats, no stack and no node pointer chasing.
+    //
+    // Two phases per round: every lane first scans on to its next entered leaf,
+    // then the lanes that called together run the (expensive) leaf test
+    // together; the warp votes keep the compiler from folding the two phases
+    // back into one divergent loop.
     const unsigned peers = __activemask();
-    int32_t stack[32];
-    stack[0] = 0;
-    CountT stack_size = 1;
-    unsigned pending = 0;                 // slots of the current node still to visit
-    int32_t kid0 = -1, kid1 = -1, kid2 = -1, kid3 = -1;
-    float ent0 = 0.f, ent1 = 0.f, ent2 = 0.f, ent3 = 0.f;
-    float ext0 = 0.f, ext1 = 0.f, ext2 = 0.f, ext3 = 0.f;
+    const mb2::PVec4 *boxes = s_.orderedBoxes;
+    const int32_t num_boxes = s_.numTraversal;
+    int32_t k = 0;
     bool walking = true;
     Entity closest = Entity::none();
     math::Vector3 closest_normal { 0, 0, 0 };
 
-    auto slab = [&](const mb2::BVHNode &node, int i, float *entry, float *exit) {
-        const float lx = inv_d.d0 * (node.minX[i] - o.x), ux = inv_d.d0 * (node.maxX[i] - o.x);
-        const float ly = inv_d.d1 * (node.minY[i] - o.y), uy = inv_d.d1 * (node.maxY[i] - o.y);
-        const float lz = inv_d.d2 * (node.minZ[i] - o.z), uz = inv_d.d2 * (node.maxZ[i] - o.z);
-        *entry = fmaxf(fminf(lx, ux), fmaxf(fminf(ly, uy), fmaxf(fminf(lz, uz), 0.f)));
-        const float far_z = fmaxf(lz, uz);
-        *exit = fminf(fmaxf(lx, ux), fminf(fmaxf(ly, uy), far_z));
-        // necessary for the full test whatever t_max is (an all-NaN exit passes)
-        return !(*entry > *exit);
-    };
-
     while (__any_sync(peers, walking)) {
         int32_t leaf_idx = -1;
         while (walking) {
-            if (pending == 0) {
-                if (stack_size == 0) {
-                    walking = false;
-                    break;
-                }
-                const mb2::BVHNode &node = s_.nodes[stack[--stack_size]];
-                kid0 = node.children[0]; kid1 = node.children[1];
-                kid2 = node.children[2]; kid3 = node.children[3];
-                const bool in0 = slab(node, 0, &ent0, &ext0), in1 = slab(node, 1, &ent1, &ext1);
-                const bool in2 = slab(node, 2, &ent2, &ext2), in3 = slab(node, 3, &ent3, &ext3);
-                pending = ((kid0 != -1 && in0) ? 1u : 0u) | ((kid1 != -1 && in1) ? 2u : 0u) |
-                          ((kid2 != -1 && in2) ? 4u : 0u) | ((kid3 != -1 && in3) ? 8u : 0u);
-                continue;
-            }
-            const int i = __ffs((int)pending) - 1;
-            pending &= pending - 1;
-            const float entry = i == 0 ? ent0 : (i == 1 ? ent1 : (i == 2 ? ent2 : ent3));
-            const float exit = i == 0 ? ext0 : (i == 1 ? ext1 : (i == 2 ? ext2 : ext3));
-            const int32_t child = i == 0 ? kid0 : (i == 1 ? kid1 : (i == 2 ? kid2 : kid3));
-            if (!(entry <= fminf(exit, t_max))) continue;
-            if (child & 0x80000000) {
-                leaf_idx = child & 0x7fffffff;
+            if (k >= num_boxes) {
+                walking = false;
                 break;
             }
-            stack[stack_size++] = child;
+            const mb2::PVec4 b0 = boxes[2 * k], b1 = boxes[2 * k + 1];
+            k += 1;
+            const float lx = inv_d.d0 * (b0.x - o.x), ux = inv_d.d0 * (b0.w - o.x);
+            const float ly = inv_d.d1 * (b0.y - o.y), uy = inv_d.d1 * (b1.x - o.y);
+            const float lz = inv_d.d2 * (b0.z - o.z), uz = inv_d.d2 * (b1.y - o.z);
+            const float entry = fmaxf(fminf(lx, ux), fmaxf(fminf(ly, uy), fmaxf(fminf(lz, uz), 0.f)));
+            const float exit = fminf(fmaxf(lx, ux), fminf(fmaxf(ly, uy), fminf(fmaxf(lz, uz), t_max)));
+            if (entry <= exit) {
+                leaf_idx = __float_as_int(b1.z);
+                break;
+            }
         }
         __syncwarp(peers);
 
