@@ -1474,7 +1474,6 @@ __device__ __forceinline__ T warpBroadcast(T v, int src)
 // arrays) are not overlapped with anything.  Four pairs in flight give four
 // independent chains per warp and keep 6 of 8 lanes busy in the face queries.
 constexpr int kGroupLanes = 8;
-constexpr int kNarrowGroups = 32 / kGroupLanes;
 
 // (separation, index) of the element the sequential scan would have kept.
 struct Winner {
@@ -1701,11 +1700,17 @@ __device__ bool hullHullGroup(EngineState &S, const PairSetup &ps, HullScratch &
 //       stride over the queue (4 pairs in flight per warp, every lane busy);
 //   orderContacts (prologue of the position solve) lists each world's hits in
 //       candidate order and assigns the dependency levels.
-constexpr int kNarrowWorldsPerBlock = 8;
+#ifndef MB2_NS_MINB
+#define MB2_NS_MINB 8      // B200, room: 6 blocks/SM (85 regs) 1.094 ms/step, 8 (64 regs) 1.074
+#endif
+#ifndef MB2_NH_MINB
+#define MB2_NH_MINB 12     // 8 (128 regs): 1.094, 12 (85): 1.074, 16 (64): 1.081
+#endif
+constexpr int kNarrowWorldsPerBlock = 8;   // 4 worlds x 64 threads: 1.105
 constexpr int kNarrowSimpleThreads = 128;
 
 template <bool SPHERE_HULL>
-__global__ void __launch_bounds__(kNarrowSimpleThreads, 6)
+__global__ void __launch_bounds__(kNarrowSimpleThreads, MB2_NS_MINB)
 physNarrowSimpleKernel(EngineState *Sp)
 {
     EngineState &S = *Sp;
@@ -1767,7 +1772,7 @@ physNarrowSimpleKernel(EngineState *Sp)
 
 constexpr int kNarrowHullThreads = 64;
 
-__global__ void __launch_bounds__(kNarrowHullThreads, 8)
+__global__ void __launch_bounds__(kNarrowHullThreads, MB2_NH_MINB)
 physNarrowHullKernel(EngineState *Sp)
 {
     EngineState &S = *Sp;
@@ -2570,7 +2575,7 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
                 const unsigned sgrid_n = (W + kNarrowWorldsPerBlock - 1) / kNarrowWorldsPerBlock;
                 if (ph->spheres) physNarrowSimpleKernel<true><<<sgrid_n, kNarrowSimpleThreads, 0, s>>>(d);
                 else physNarrowSimpleKernel<false><<<sgrid_n, kNarrowSimpleThreads, 0, s>>>(d);
-                physNarrowHullKernel<<<(unsigned)ex->numSMs * 8u, kNarrowHullThreads, 0, s>>>(d);
+                physNarrowHullKernel<<<(unsigned)ex->numSMs * (unsigned)MB2_NH_MINB, kNarrowHullThreads, 0, s>>>(d);
             }
             break;
         case NodePhysSolvePositions:
