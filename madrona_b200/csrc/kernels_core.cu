@@ -5,10 +5,13 @@
 
 namespace mb2 {
 
+bool g_pdl = false;
+
 // ClearTmpNode: drop every row of a temporary archetype (numRows.exchange(0)
 // in the reference) and zero its per-world counts.
 __global__ void clearTmpKernel(EngineState *S, uint32_t archetype)
 {
+    pdlSync();
     TableDesc &t = S->tables[archetype];
     const int32_t W = (int32_t)S->numWorlds;
     for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
@@ -22,11 +25,16 @@ __global__ void clearTmpKernel(EngineState *S, uint32_t archetype)
     }
 }
 
-__global__ void resetTmpAllocKernel(EngineState *S) { S->tmpOffset = 0; }
+__global__ void resetTmpAllocKernel(EngineState *S)
+{
+    pdlSync();
+    S->tmpOffset = 0;
+}
 
 // Last node of every launch graph: publish error flags to pinned host memory.
 __global__ void statusCopyKernel(EngineState *S, uint32_t *host_status)
 {
+    pdlSync();
     host_status[0] = S->errorFlags;
     host_status[1] = S->errorArchetype;
 }
@@ -36,6 +44,7 @@ __global__ void statusCopyKernel(EngineState *S, uint32_t *host_status)
 // entity IDs follow the CPU backend's init cache: order * W + world.
 __global__ void fillSingletonsKernel(EngineState *S)
 {
+    pdlSync();
     const int32_t W = (int32_t)S->numWorlds;
     for (uint32_t a = 0; a < S->numArchetypes; a++) {
         const ArchetypeInfo &info = S->archetypes[a];
@@ -58,23 +67,23 @@ __global__ void fillSingletonsKernel(EngineState *S)
 void launchClearTmp(Executor *ex, uint32_t archetype, cudaStream_t s)
 {
     int grid = (int)std::min<uint32_t>((ex->hState->numWorlds + 255) / 256, (uint32_t)ex->numSMs * 2);
-    clearTmpKernel<<<std::max(grid, 1), 256, 0, s>>>(ex->dState, archetype);
+    launchK(clearTmpKernel, dim3(std::max(grid, 1)), dim3(256), 0, s, ex->dState, archetype);
 }
 
 void launchResetTmpAlloc(Executor *ex, cudaStream_t s)
 {
-    resetTmpAllocKernel<<<1, 1, 0, s>>>(ex->dState);
+    launchK(resetTmpAllocKernel, dim3(1), dim3(1), 0, s, ex->dState);
 }
 
 void launchStatusCopy(Executor *ex, cudaStream_t s)
 {
-    statusCopyKernel<<<1, 1, 0, s>>>(ex->dState, ex->hStatus);
+    launchK(statusCopyKernel, dim3(1), dim3(1), 0, s, ex->dState, ex->hStatus);
 }
 
 void launchFillSingletons(Executor *ex, cudaStream_t s)
 {
     int grid = (int)std::min<uint32_t>((ex->hState->numWorlds + 255) / 256, (uint32_t)ex->numSMs * 2);
-    fillSingletonsKernel<<<std::max(grid, 1), 256, 0, s>>>(ex->dState);
+    launchK(fillSingletonsKernel, dim3(std::max(grid, 1)), dim3(256), 0, s, ex->dState);
 }
 
 }

@@ -1713,6 +1713,7 @@ template <bool SPHERE_HULL>
 __global__ void __launch_bounds__(kNarrowSimpleThreads, MB2_NS_MINB)
 physNarrowSimpleKernel(EngineState *Sp)
 {
+    pdlSync();
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
     __shared__ i32 first[kNarrowWorldsPerBlock + 1];
@@ -1775,6 +1776,7 @@ constexpr int kNarrowHullThreads = 64;
 __global__ void __launch_bounds__(kNarrowHullThreads, MB2_NH_MINB)
 physNarrowHullKernel(EngineState *Sp)
 {
+    pdlSync();
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
     __shared__ HullScratch scratch[kNarrowHullThreads / kGroupLanes];
@@ -2335,6 +2337,7 @@ template <u32 OP>
 __global__ void __launch_bounds__(256)
 physBodyKernel(EngineState *Sp)
 {
+    pdlSync();
     const EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
     if (blockIdx.y >= P.numBodyArchetypes) return;
@@ -2361,6 +2364,7 @@ physBodyKernel(EngineState *Sp)
 __global__ void __launch_bounds__(128)
 physRebuildKernel(EngineState *Sp)
 {
+    pdlSync();
     const EngineState &S = *Sp;
     const i32 w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= (i32)S.numWorlds) return;
@@ -2397,6 +2401,7 @@ template <u32 OP>
 __global__ void __launch_bounds__(32 * kPhysWarps, physMinBlocks(OP))
 physWorldKernel(EngineState *Sp)
 {
+    pdlSync();
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
     const int lane = threadIdx.x & 31;
@@ -2558,34 +2563,34 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
             // tag 0 (post-integration) never rebuilds in the reference either; a
             // pending rebuild request then simply waits for the next tag-1 node,
             // and the un-refitted leaves are refitted by that rebuild
-            physBodyKernel<PhaseUpdateLeaves><<<bgrid, 256, 0, s>>>(d);
-            if (rec.userTag == 1) physRebuildKernel<<<(W + 127) / 128, 128, 0, s>>>(d);
+            launchK(physBodyKernel<PhaseUpdateLeaves>, dim3(bgrid), dim3(256), 0, s, d);
+            if (rec.userTag == 1) launchK(physRebuildKernel, dim3((W + 127) / 128), dim3(128), 0, s, d);
             break;
         case NodePhysFindCandidates:
             // joints are iterated per world by the solver: keep their table in
             // world order (the reference sorts Joint here too, xpbd.cpp:1092-1096)
             launchSortArchetype(ex, ph->hPhys.jointArchetype, 1, s);
-            physWorldKernel<PhaseFindCandidates><<<wgrid, wblock, 0, s>>>(d);
+            launchK(physWorldKernel<PhaseFindCandidates>, dim3(wgrid), dim3(wblock), 0, s, d);
             break;
         case NodePhysSubstepBegin:
-            physBodyKernel<PhaseIntegrate><<<bgrid, 256, 0, s>>>(d);
+            launchK(physBodyKernel<PhaseIntegrate>, dim3(bgrid), dim3(256), 0, s, d);
             break;
         case NodePhysNarrowphase:
             {
                 const unsigned sgrid_n = (W + kNarrowWorldsPerBlock - 1) / kNarrowWorldsPerBlock;
-                if (ph->spheres) physNarrowSimpleKernel<true><<<sgrid_n, kNarrowSimpleThreads, 0, s>>>(d);
-                else physNarrowSimpleKernel<false><<<sgrid_n, kNarrowSimpleThreads, 0, s>>>(d);
-                physNarrowHullKernel<<<(unsigned)ex->numSMs * (unsigned)MB2_NH_MINB, kNarrowHullThreads, 0, s>>>(d);
+                if (ph->spheres) launchK(physNarrowSimpleKernel<true>, dim3(sgrid_n), dim3(kNarrowSimpleThreads), 0, s, d);
+                else launchK(physNarrowSimpleKernel<false>, dim3(sgrid_n), dim3(kNarrowSimpleThreads), 0, s, d);
+                launchK(physNarrowHullKernel, dim3((unsigned)ex->numSMs * (unsigned)MB2_NH_MINB), dim3(kNarrowHullThreads), 0, s, d);
             }
             break;
         case NodePhysSolvePositions:
-            physWorldKernel<PhaseSolvePositions><<<sgrid, wblock, 0, s>>>(d);
+            launchK(physWorldKernel<PhaseSolvePositions>, dim3(sgrid), dim3(wblock), 0, s, d);
             break;
         case NodePhysSetVelocities:
-            physBodyKernel<PhaseSetVelocities><<<bgrid, 256, 0, s>>>(d);
+            launchK(physBodyKernel<PhaseSetVelocities>, dim3(bgrid), dim3(256), 0, s, d);
             break;
         case NodePhysSolveVelocities:
-            physWorldKernel<PhaseSolveVelocities><<<sgrid, wblock, 0, s>>>(d);
+            launchK(physWorldKernel<PhaseSolveVelocities>, dim3(sgrid), dim3(wblock), 0, s, d);
             break;
         default:
             *err = "unknown physics node kind " + std::to_string(rec.kind);

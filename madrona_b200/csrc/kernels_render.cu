@@ -56,6 +56,7 @@ constexpr int kStagedInstances = 64;
 __global__ void __launch_bounds__(128)
 renderGatherInstancesKernel(EngineState *Sp)
 {
+    pdlSync();
     EngineState &S = *Sp;
     RenderState &R = *S.render;
     const int lane = threadIdx.x & 31;
@@ -116,6 +117,7 @@ renderGatherInstancesKernel(EngineState *Sp)
 __global__ void __launch_bounds__(256)
 renderGatherViewsKernel(EngineState *Sp)
 {
+    pdlSync();
     EngineState &S = *Sp;
     RenderState &R = *S.render;
     if (blockIdx.y >= R.numViewArchetypes) return;
@@ -281,6 +283,7 @@ constexpr int kTriArena = 640;      // origin-relative triangles staged per bloc
 __global__ void __launch_bounds__(256, 4)
 renderRaycastKernel(EngineState *Sp)
 {
+    pdlSync();
     EngineState &S = *Sp;
     const RenderState &R = *S.render;
     const TableDesc &out_tbl = S.tables[R.outputArchetype];
@@ -656,14 +659,14 @@ bool renderEnqueuePrepare(Executor *ex, cudaStream_t s, std::string *err)
     if (!rh || !rh->active) return true;   // rendering not configured: nothing to prepare
     (void)err;
     const unsigned W = ex->hState->numWorlds;
-    renderGatherInstancesKernel<<<(W * 32 + 127) / 128, 128, 0, s>>>(ex->dState);
+    launchK(renderGatherInstancesKernel, dim3((W * 32 + 127) / 128), dim3(128), 0, s, ex->dState);
     int max_cap = 256;
     for (u32 i = 0; i < rh->hRender.numViewArchetypes; i++) {
         max_cap = std::max(max_cap, ex->hState->tables[rh->hRender.viewers[i].archetype].capacity);
     }
     dim3 grid((unsigned)std::min((max_cap + 255) / 256, ex->numSMs * 4),
               std::max(rh->hRender.numViewArchetypes, 1u));
-    renderGatherViewsKernel<<<grid, 256, 0, s>>>(ex->dState);
+    launchK(renderGatherViewsKernel, dim3(grid), dim3(256), 0, s, ex->dState);
     return true;
 }
 
@@ -686,7 +689,7 @@ LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err)
         return nullptr;
     }
     const unsigned view_blocks = (unsigned)std::max(1, std::min(R.maxViews, 65535));
-    renderRaycastKernel<<<dim3(1, view_blocks), 256, 0, ex->stream>>>(ex->dState);
+    launchK(renderRaycastKernel, dim3(1, view_blocks), dim3(256), 0, ex->stream, ex->dState);
     launchStatusCopy(ex, ex->stream);
     cudaError_t e = cudaStreamEndCapture(ex->stream, &g->graph);
     if (e != cudaSuccess || cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) {

@@ -86,6 +86,7 @@ __device__ __forceinline__ uint32_t loadKey(const TableDesc &t, int32_t col, int
 __global__ void __launch_bounds__(kSortThreads)
 sortHistogramKernel(SortParams p)
 {
+    pdlSync();
     const TableDesc &t = p.state->tables[p.archetype];
     if (!sortActive(p, t)) return;
     const int32_t n = t.numRows;
@@ -123,6 +124,7 @@ constexpr uint32_t kValueMask = (1u << 30) - 1u;
 __global__ void __launch_bounds__(kSortThreads)
 sortOnesweepKernel(SortParams p, int pass)
 {
+    pdlSync();
     const TableDesc &t = p.state->tables[p.archetype];
     if (!sortActive(p, t)) return;
     const int32_t n = t.numRows;
@@ -323,6 +325,7 @@ __device__ __forceinline__ void gatherTile(const void *src_v, void *dst_v, const
 __global__ void __launch_bounds__(256)
 sortRearrangeKernel(SortParams p)
 {
+    pdlSync();
     TableDesc &t = p.state->tables[p.archetype];
     if (!sortActive(p, t)) return;
     const int32_t n = t.numRows;
@@ -435,6 +438,7 @@ sortRearrangeKernel(SortParams p)
 __global__ void __launch_bounds__(256)
 sortCopyBackKernel(SortParams p, unsigned long long exported_mask)
 {
+    pdlSync();
     TableDesc &t = p.state->tables[p.archetype];
     if (!p.ctrl->didSort) return;
     const int32_t n = t.numRows;
@@ -595,17 +599,17 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
         return (v && *v) ? std::max(1, atoi(v)) : 4;   // B200, 3.1M rows: 2 -> 0.659, 3 -> 0.615, 4 -> 0.598, 6 -> 0.599 ms
     }();
     const int sweep_grid = std::max(1, std::min(tiles, ex->numSMs * sweep_per_sm));
-    sortHistogramKernel<<<hist_grid, kSortThreads, 0, s>>>(p);
+    launchK(sortHistogramKernel, dim3(hist_grid), dim3(kSortThreads), 0, s, p);
     for (int pass = 0; pass < p.numPasses; pass++) {
-        sortOnesweepKernel<<<sweep_grid, kSortThreads, 0, s>>>(p, pass);
+        launchK(sortOnesweepKernel, dim3(sweep_grid), dim3(kSortThreads), 0, s, p, pass);
     }
     const int rtiles = (t.capacity + kRearrangeTile - 1) / kRearrangeTile;
     const int rblocks = std::max(1, std::min(rtiles, ex->numSMs * 4));
-    sortRearrangeKernel<<<rblocks, 256, 0, s>>>(p);
+    launchK(sortRearrangeKernel, dim3(rblocks), dim3(256), 0, s, p);
     const int row_blocks = std::max(1, std::min((t.capacity + 255) / 256, ex->numSMs * 2));
     dim3 rgrid((unsigned)row_blocks, (unsigned)t.numColumns);
 
-    if (mask) sortCopyBackKernel<<<rgrid, 256, 0, s>>>(p, mask);
+    if (mask) launchK(sortCopyBackKernel, dim3(rgrid), dim3(256), 0, s, p, mask);
 }
 
 }
