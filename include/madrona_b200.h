@@ -126,6 +126,12 @@ int64_t mb2_get_exported_row_bytes(const mb2_executor *exec, int64_t slot);
 /* Kernel nodes inside a built launch graph (== launches per run). */
 int64_t mb2_launch_graph_num_kernels(const mb2_launch_graph *graph);
 
+/* Capture streams the launch graph was built from: > 1 means TaskGraph nodes
+ * that do not depend on each other (TaskGraphBuilder::addToGraph dependency
+ * lists, include/madrona/taskgraph_builder.hpp:128-140) became parallel
+ * branches of the CUDA graph. */
+int64_t mb2_launch_graph_num_branches(const mb2_launch_graph *graph);
+
 /* The stream mb2_run launches on (cudaStream_t). */
 void *mb2_executor_stream(mb2_executor *exec);
 

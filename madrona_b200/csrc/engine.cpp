@@ -519,12 +519,22 @@ static LaunchGraph *buildGraph(Executor *ex, const uint32_t *ids, uint32_t n, co
     g->name = name ? name : "";
 
     physicsBeforeGraphCapture(ex);
-    cudaError_t e = cudaStreamBeginCapture(ex->stream, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) {
-        setError(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
-        delete g;
-        return nullptr;
-    }
+
+    // ---- units of work: one TaskGraph node each, except that a run of consecutive
+    // physics nodes is one (internally ordered) unit.  Units keep the simulator's
+    // dependency lists (reference: TaskGraphBuilder::build, src/core/taskgraph.cpp:
+    // 53-117 -- a dependency can only name an earlier node, so registration order
+    // is a topological order); units that do not depend on each other are captured
+    // on different streams and become parallel branches of the CUDA graph.
+    struct Unit {
+        uint32_t first, last;
+        bool usesSortScratch;
+        std::vector<int> deps;      // unit indices
+        int stream = -1;
+        cudaEvent_t done = nullptr;
+    };
+    std::vector<Unit> units;
+    std::vector<int> unit_of_node(S.numNodes, -1);
     bool ok = true;
     for (uint32_t i = 0; i < n && ok; i++) {
         if (ids[i] >= S.numTaskGraphs) {
@@ -532,27 +542,125 @@ static LaunchGraph *buildGraph(Executor *ex, const uint32_t *ids, uint32_t n, co
             ok = false;
             break;
         }
-        for (uint32_t node = 0; node < S.numNodes && ok; node++) {
+        const size_t first_unit_of_graph = units.size();
+        for (uint32_t node = 0; node < S.numNodes; node++) {
             if (S.nodes[node].taskgraph != ids[i]) continue;
-            if (S.nodes[node].kind >= NodePhysBroadphaseUpdate && S.nodes[node].kind < NodeRenderPrepare) {
-                // a run of consecutive physics nodes is one fused launch
-                uint32_t last = node;
-                while (last + 1 < S.numNodes && S.nodes[last + 1].taskgraph == ids[i] &&
-                       S.nodes[last + 1].kind >= NodePhysBroadphaseUpdate &&
-                       S.nodes[last + 1].kind < NodeRenderPrepare) {
-                    last++;
+            auto is_phys = [&](uint32_t k) {
+                return S.nodes[k].kind >= NodePhysBroadphaseUpdate && S.nodes[k].kind < NodeRenderPrepare;
+            };
+            Unit u;
+            u.first = u.last = node;
+            if (is_phys(node)) {
+                while (u.last + 1 < S.numNodes && S.nodes[u.last + 1].taskgraph == ids[i] && is_phys(u.last + 1)) {
+                    u.last++;
                 }
-                std::string perr;
-                ok = physicsEnqueueNodes(ex, &S.nodes[node], last - node + 1, ex->stream, &perr);
-                if (!ok) setError(perr);
-                node = last;
-                continue;
             }
-            ok = enqueueNode(ex, node, ex->stream);
+            u.usesSortScratch = false;
+            for (uint32_t k = u.first; k <= u.last; k++) {
+                const uint32_t kind = S.nodes[k].kind;
+                if (kind == NodeSortArchetype || kind == NodeCompactArchetype || kind == NodePhysFindCandidates ||
+                        kind == NodeRenderPrepare) {
+                    u.usesSortScratch = true;     // one scratch block serves every sort: keep them in line
+                }
+                unit_of_node[k] = (int)units.size();
+            }
+            for (uint32_t k = u.first; k <= u.last; k++) {
+                const NodeRecord &r = S.nodes[k];
+                for (uint32_t d = 0; d < r.numDeps && d < (uint32_t)kMaxNodeDeps; d++) {
+                    const uint32_t dep_node = r.deps[d];
+                    if (dep_node >= S.numNodes || unit_of_node[dep_node] < 0) continue;
+                    const int du = unit_of_node[dep_node];
+                    if (du == (int)units.size() || du < (int)first_unit_of_graph) continue;
+                    if (std::find(u.deps.begin(), u.deps.end(), du) == u.deps.end()) u.deps.push_back(du);
+                }
+            }
+            if (u.usesSortScratch) {
+                for (int k = (int)units.size() - 1; k >= (int)first_unit_of_graph; k--) {
+                    if (units[k].usesSortScratch) {
+                        if (std::find(u.deps.begin(), u.deps.end(), k) == u.deps.end()) u.deps.push_back(k);
+                        break;
+                    }
+                }
+            }
+            // task graphs of one launch graph run one after the other
+            if (u.deps.empty() && first_unit_of_graph > 0) {
+                for (size_t k = 0; k < first_unit_of_graph; k++) u.deps.push_back((int)k);
+            }
+            node = u.last;
+            units.push_back(std::move(u));
         }
+    }
+    const bool branches = envU64("MADRONA_B200_GRAPH_BRANCHES", 1) != 0;
+
+    cudaError_t e = cudaStreamBeginCapture(ex->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        setError(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+        delete g;
+        return nullptr;
+    }
+    // stream 0 = the capture origin; side streams join the capture through events
+    std::vector<cudaStream_t> streams { ex->stream };
+    std::vector<int> tail { -1 };              // last unit placed on each stream
+    cudaEvent_t origin_start = nullptr;
+    cudaEventCreateWithFlags(&origin_start, cudaEventDisableTiming);
+    cudaEventRecord(origin_start, ex->stream);
+    std::vector<cudaEvent_t> events { origin_start };
+
+    for (size_t ui = 0; ui < units.size() && ok; ui++) {
+        Unit &u = units[ui];
+        int chosen = -1;
+        if (!branches) {
+            chosen = 0;
+        } else {
+            // continue on the stream of a dependency that is still that stream's tail
+            for (int d : u.deps) {
+                if (tail[units[d].stream] == d) {
+                    chosen = units[d].stream;
+                    break;
+                }
+            }
+            if (chosen < 0 && tail[0] == -1) chosen = 0;
+            if (chosen < 0) {
+                // a free side stream (its tail is an ancestor everybody already waited for) or a new one
+                cudaStream_t ns = nullptr;
+                if (cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking) != cudaSuccess) {
+                    chosen = 0;
+                } else {
+                    streams.push_back(ns);
+                    tail.push_back(-1);
+                    chosen = (int)streams.size() - 1;
+                    cudaStreamWaitEvent(ns, origin_start, 0);
+                }
+            }
+        }
+        u.stream = chosen;
+        cudaStream_t cs = streams[chosen];
+        for (int d : u.deps) {
+            if (units[d].stream != chosen || !branches) {
+                if (units[d].stream != chosen) cudaStreamWaitEvent(cs, units[d].done, 0);
+            }
+        }
+        if (u.last > u.first) {
+            std::string perr;
+            ok = physicsEnqueueNodes(ex, &S.nodes[u.first], u.last - u.first + 1, cs, &perr);
+            if (!ok) setError(perr);
+        } else {
+            ok = enqueueNode(ex, u.first, cs);
+        }
+        cudaEventCreateWithFlags(&u.done, cudaEventDisableTiming);
+        cudaEventRecord(u.done, cs);
+        events.push_back(u.done);
+        tail[chosen] = (int)ui;
+    }
+    // join every side stream back into the origin
+    for (size_t si = 1; si < streams.size(); si++) {
+        if (tail[si] >= 0) cudaStreamWaitEvent(ex->stream, units[tail[si]].done, 0);
     }
     if (ok) launchStatusCopy(ex, ex->stream);
     e = cudaStreamEndCapture(ex->stream, &g->graph);
+    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+    for (size_t si = 1; si < streams.size(); si++) cudaStreamDestroy(streams[si]);
+    g->numBranches = (int64_t)streams.size();
     if (!ok || e != cudaSuccess) {
         if (ok) setError(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
         if (g->graph) cudaGraphDestroy(g->graph);
@@ -862,6 +970,11 @@ int64_t mb2_get_exported_row_bytes(const mb2_executor *exec, int64_t slot)
 int64_t mb2_launch_graph_num_kernels(const mb2_launch_graph *graph)
 {
     return graph ? ((const LaunchGraph *)graph)->numKernels : -1;
+}
+
+int64_t mb2_launch_graph_num_branches(const mb2_launch_graph *graph)
+{
+    return graph ? ((const LaunchGraph *)graph)->numBranches : -1;
 }
 
 void *mb2_executor_stream(mb2_executor *exec)

@@ -47,6 +47,7 @@ struct LaunchGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t numKernels = 0;
+    int64_t numBranches = 1;   // capture streams used (parallel branches of independent nodes)
     std::string name;
 };
 

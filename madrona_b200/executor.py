@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "mb2_get_exported_num_rows",
     "mb2_get_exported_row_bytes",
     "mb2_launch_graph_num_kernels",
+    "mb2_launch_graph_num_branches",
     "mb2_executor_stream",
     "mb2_jit_precompile",
     "mb2_profile_nodes",
@@ -137,6 +138,8 @@ def load_library() -> ctypes.CDLL:
     lib.mb2_get_exported_row_bytes.restype = ctypes.c_int64
     lib.mb2_launch_graph_num_kernels.argtypes = [vp]
     lib.mb2_launch_graph_num_kernels.restype = ctypes.c_int64
+    lib.mb2_launch_graph_num_branches.argtypes = [vp]
+    lib.mb2_launch_graph_num_branches.restype = ctypes.c_int64
     lib.mb2_executor_stream.argtypes = [vp]
     lib.mb2_executor_stream.restype = vp
     lib.mb2_jit_precompile.argtypes = [ctypes.POINTER(_CompileConfigC)]
@@ -227,6 +230,10 @@ class MWCudaLaunchGraph:
     @property
     def num_kernels(self) -> int:
         return int(self._lib.mb2_launch_graph_num_kernels(self._h))
+
+    @property
+    def num_branches(self) -> int:
+        return int(self._lib.mb2_launch_graph_num_branches(self._h))
 
     def __del__(self):
         try:

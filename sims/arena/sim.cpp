@@ -564,18 +564,20 @@ void Sim::setupTasks(TaskGraphManager &mgr, const Config &)
 #endif
     auto post_bvh = PhysicsSystem::setupBroadphaseTasks(builder, {post_reset});
 
-    auto self_obs = builder.addToGraph<ParallelForNode<Engine, selfObsSystem,
+    // three independent observation systems (they only read the world): parallel
+    // branches of the step graph on the GPU
+    builder.addToGraph<ParallelForNode<Engine, selfObsSystem,
         Position, Rotation, Team, Grip, StepsRemaining, SelfObs>>({post_bvh});
 #ifdef MADRONA_GPU_MODE
-    auto other_obs = builder.addToGraph<CustomParallelForNode<Engine, otherObsSystem, 8, 1,
-        Entity, Position, OtherObs>>({self_obs});
+    builder.addToGraph<CustomParallelForNode<Engine, otherObsSystem, 8, 1,
+        Entity, Position, OtherObs>>({post_bvh});
     builder.addToGraph<CustomParallelForNode<Engine, lidarSystem, kNumLidar, 1,
-        Entity, Position, Rotation, Lidar>>({other_obs});
+        Entity, Position, Rotation, Lidar>>({post_bvh});
 #else
-    auto other_obs = builder.addToGraph<ParallelForNode<Engine, otherObsSystem,
-        Entity, Position, OtherObs>>({self_obs});
+    builder.addToGraph<ParallelForNode<Engine, otherObsSystem,
+        Entity, Position, OtherObs>>({post_bvh});
     builder.addToGraph<ParallelForNode<Engine, lidarSystem,
-        Entity, Position, Rotation, Lidar>>({other_obs});
+        Entity, Position, Rotation, Lidar>>({post_bvh});
 #endif
 }
 

@@ -355,12 +355,13 @@ void Sim::setupTasks(TaskGraphManager &mgr, const Config &)
 
     auto obs = builder.addToGraph<ParallelForNode<Engine, observationSystem,
         Position, Rotation, Progress, StepsRemaining, SelfObs>>({post_bvh});
+    // independent of the observation system: a parallel branch of the step graph on the GPU
 #ifdef MADRONA_GPU_MODE
     builder.addToGraph<CustomParallelForNode<Engine, lidarSystem, kNumLidar, 1,
-        Entity, Position, Rotation, Lidar>>({obs});
+        Entity, Position, Rotation, Lidar>>({post_bvh});
 #else
     builder.addToGraph<ParallelForNode<Engine, lidarSystem,
-        Entity, Position, Rotation, Lidar>>({obs});
+        Entity, Position, Rotation, Lidar>>({post_bvh});
 #endif
 #ifdef ROOM_ENABLE_RENDER
     render::RenderingSystem::setupTasks(builder, {obs});

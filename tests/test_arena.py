@@ -64,6 +64,29 @@ def test_gpu_matches_golden():
 
 
 @pytest.mark.gpu
+def test_independent_nodes_become_graph_branches(monkeypatch):
+    # selfObs / otherObs / lidar only depend on the post-reset broadphase update
+    # (sims/arena/sim.cpp setupTasks): the step graph must fork, and forking must not
+    # change a bit of the result
+    from sims import make_executor
+    W, steps, ins, outs = load_golden("arena_w2_s200")
+    ex = make_executor("arena", W, **CFG)
+    g = ex.buildLaunchGraphAllTaskGraphs()
+    assert g.num_branches >= 3
+    del g
+    ex.close()
+    monkeypatch.setenv("MADRONA_B200_GRAPH_BRANCHES", "0")
+    ex = make_executor("arena", W, **CFG)
+    g = ex.buildLaunchGraphAllTaskGraphs()
+    assert g.num_branches == 1
+    del g
+    ex.close()
+    short = {k: v[:40] for k, v in ins.items()}
+    got, _ = rollout_gpu("arena", W, 40, short, CFG)
+    assert_traces_equal(got, {k: v[:41] for k, v in outs.items()}, exact=EXACT, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
 @pytest.mark.skipif(not runner.available("arena"), reason="oracle/_ref not built")
 def test_gpu_matches_live_reference_many_worlds():
     W, steps = 160, 150
