@@ -52,25 +52,72 @@ typedef struct mb2_compile_config {
     uint32_t opt_mode;
 } mb2_compile_config;
 
-/* == madrona::CudaBatchRenderConfig, include/madrona/mw_gpu.hpp:75-96, with
- * render::MeshBVHData flattened to plain device/host arrays
- * (include/madrona/render/cuda_batch_render_assets.hpp). */
+/* == render::MeshBVHData / render::MaterialData
+ * (include/madrona/render/cuda_batch_render_assets.hpp): DEVICE pointers to
+ * reference-format arrays -- QBVHNode (60 B), MeshBVH::LeafMaterial,
+ * MeshBVH::BVHVertex (20 B), MeshBVH (72 B), Material (28 B); layouts in
+ * madrona_b200/csrc/render_bvh.h.  What render::AssetProcessor::makeBVHData
+ * returns can be passed as is; mb2_build_mesh_bvhs builds the same from
+ * triangle meshes. */
+typedef struct mb2_mesh_bvh_view {
+    void *nodes;
+    uint64_t num_nodes;
+    void *leaf_material;
+    uint64_t num_leaves;
+    void *vertices;
+    uint64_t num_verts;
+    void *mesh_bvhs;
+    uint64_t num_bvhs;
+} mb2_mesh_bvh_view;
+
+typedef struct mb2_material_view {
+    void *textures;                /* cudaTextureObject_t *: textures are not sampled by this engine */
+    uint32_t num_texture_buffers;
+    void *texture_buffers;
+    void *materials;               /* madrona::Material * (device) or NULL */
+} mb2_material_view;
+
+/* == madrona::CudaBatchRenderConfig, include/madrona/mw_gpu.hpp:75-96 (same
+ * fields, same order). */
 typedef struct mb2_render_config {
     uint32_t render_mode;          /* 0 RGBD, 1 Depth */
+    mb2_mesh_bvh_view geo_bvh_data;
+    mb2_material_view material_data;
     uint32_t render_resolution;    /* square output */
     float near_plane;
     float far_plane;
-    const void *mesh_bvhs;         /* host array of mb2 mesh descriptors */
-    uint32_t num_mesh_bvhs;
-    const void *vertices;          /* host float[3*num_vertices] */
-    uint32_t num_vertices;
-    const void *indices;           /* host uint32[3*num_triangles] */
-    uint32_t num_triangles;
 } mb2_render_config;
+
+/* Triangle mesh -> BLAS.  Role of MeshBVHBuilder (src/common/mesh_bvh_builder.cpp,
+ * embree based) + render::AssetProcessor::makeBVHData (src/render/
+ * asset_processor.cpp): one reference-format MeshBVH per mesh, arrays
+ * concatenated, uploaded to gpu_id (gpu_id < 0: host only).  uvs may be NULL.
+ * mb2_mesh_bvh_data_view returns a pointer to an mb2_mesh_bvh_view with device
+ * (device != 0) or host pointers; mb2_mesh_bvh_triangle_sources maps every
+ * triangle of the concatenated BLAS order back to its index in its source mesh. */
+typedef struct mb2_mesh_source {
+    const float *positions;        /* xyz per vertex */
+    const float *uvs;              /* uv per vertex or NULL */
+    uint32_t num_vertices;
+    const uint32_t *indices;       /* 3 per triangle */
+    uint32_t num_triangles;
+    int32_t material_idx;          /* -1: none (white) */
+} mb2_mesh_source;
+typedef struct mb2_mesh_bvh_data mb2_mesh_bvh_data;
+mb2_mesh_bvh_data *mb2_build_mesh_bvhs(const mb2_mesh_source *meshes, uint32_t num_meshes, int gpu_id);
+const void *mb2_mesh_bvh_data_view(const mb2_mesh_bvh_data *data, int device);
+const uint32_t *mb2_mesh_bvh_triangle_sources(const mb2_mesh_bvh_data *data);
+void mb2_mesh_bvh_data_destroy(mb2_mesh_bvh_data *data);
 
 /* MWCudaExecutor::initCUDA(int gpu_id), mw_gpu.hpp:122 / cuda_exec.cpp:2315.
  * Returns 0 on success. */
 int mb2_init_cuda(int gpu_id);
+
+/* Same, also returning the device's primary CUcontext (what
+ * MWCudaExecutor::initCUDA hands back to the Manager), and the inverse lookup
+ * (context -> device ordinal; NULL -> the current device). */
+int mb2_init_cuda_ctx(int gpu_id, void **cu_context_out);
+int mb2_device_of_context(void *cu_context);
 
 /* MWCudaExecutor::MWCudaExecutor(const StateConfig&, const CompileConfig&,
  * CUcontext, const Optional<CudaBatchRenderConfig>&), mw_gpu.hpp:125-129 /
@@ -122,6 +169,19 @@ int64_t mb2_get_exported_num_rows(mb2_executor *exec, int64_t slot);
 
 /* Bytes per row of the exported component. */
 int64_t mb2_get_exported_row_bytes(const mb2_executor *exec, int64_t slot);
+
+/* With MADRONA_B200_RENDER_DEBUG=1 at executor creation: device pointer to
+ * int32 [views][res * res][2] = (instance index inside its world, triangle
+ * index inside the instance's mesh BLAS order) of every pixel's closest hit,
+ * -1 for a miss; NULL otherwise.  Test hook of the ray caster. */
+void *mb2_render_debug_hits(mb2_executor *exec);
+
+/* Test hook: the ray caster's per-world structures of the last render-prepare.
+ * which = 1: QBVHNode [worlds][max_instances] (TLAS, node 0 = root), 2: int32
+ * TLAS node counts [worlds], 3: instances [worlds][max_instances] (76-byte
+ * records: position, rotation, scale, matID, objectID, colour, world box),
+ * 4: int32 instance counts [worlds].  Device pointers; NULL without a renderer. */
+void *mb2_render_debug_buffer(mb2_executor *exec, int which, int64_t *max_instances_per_world);
 
 /* Kernel nodes inside a built launch graph (== launches per run). */
 int64_t mb2_launch_graph_num_kernels(const mb2_launch_graph *graph);

@@ -16,5 +16,7 @@ from .executor import (  # noqa: F401
     load_library,
     library_path,
     precompile,
+    MeshBVHData,
+    PeerGather,
 )
 from .tensor import Tensor, TensorElementType  # noqa: F401

@@ -820,6 +820,16 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
 
 using namespace mb2;
 
+// driver entry points through the runtime (no link dependency on libcuda)
+template <typename Fn>
+static Fn driverFn(const char *name)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return (Fn)fn;
+}
+
 extern "C" {
 
 int64_t mb2_profile_nodes(mb2_executor *exec, const uint32_t *taskgraph_ids,
@@ -852,6 +862,38 @@ int mb2_init_cuda(int gpu_id)
     }
     cudaFree(nullptr);
     return 0;
+}
+
+int mb2_init_cuda_ctx(int gpu_id, void **cu_context_out)
+{
+    if (mb2_init_cuda(gpu_id) != 0) return 1;
+    if (cu_context_out) {
+        *cu_context_out = nullptr;
+        auto retain = driverFn<int (*)(void **, int)>("cuDevicePrimaryCtxRetain");
+        auto dev_get = driverFn<int (*)(int *, int)>("cuDeviceGet");
+        int dev = 0;
+        if (!retain || !dev_get || dev_get(&dev, gpu_id) != 0 || retain(cu_context_out, dev) != 0) {
+            setError("cuDevicePrimaryCtxRetain failed");
+            return 1;
+        }
+    }
+    return 0;
+}
+
+int mb2_device_of_context(void *cu_context)
+{
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (!cu_context) return cur;
+    auto push = driverFn<int (*)(void *)>("cuCtxPushCurrent");
+    auto pop = driverFn<int (*)(void **)>("cuCtxPopCurrent");
+    auto get_dev = driverFn<int (*)(int *)>("cuCtxGetDevice");
+    if (!push || !pop || !get_dev || push(cu_context) != 0) return cur;
+    int dev = cur;
+    get_dev(&dev);
+    void *old = nullptr;
+    pop(&old);
+    return dev;
 }
 
 mb2_executor *mb2_executor_create(const mb2_state_config *state_cfg,
@@ -970,6 +1012,19 @@ int64_t mb2_get_exported_row_bytes(const mb2_executor *exec, int64_t slot)
 int64_t mb2_launch_graph_num_kernels(const mb2_launch_graph *graph)
 {
     return graph ? ((const LaunchGraph *)graph)->numKernels : -1;
+}
+
+void *mb2_render_debug_hits(mb2_executor *exec)
+{
+    return exec ? renderDebugHitBuffer((Executor *)exec) : nullptr;
+}
+
+void *mb2_render_debug_buffer(mb2_executor *exec, int which, int64_t *max_instances_per_world)
+{
+    int64_t stride = 0;
+    void *p = exec ? renderDebugBuffer((Executor *)exec, which, &stride) : nullptr;
+    if (max_instances_per_world) *max_instances_per_world = stride;
+    return p;
 }
 
 int64_t mb2_launch_graph_num_branches(const mb2_launch_graph *graph)

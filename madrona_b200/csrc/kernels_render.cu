@@ -1,32 +1,48 @@
 // kernels_render.cu -- hot system 3: batch ray-cast renderer (SURVEY.md 8 rows
-// a13-a15).  Per step (render-prepare node, inside the step graph): gather
-// every world's renderable instances (transform, object, world-space box) and
-// every view's camera into flat arrays.  Render graph: one thread per pixel,
-// a block covers 256 consecutive pixels of ONE view, so all its rays walk the
-// same world's instance list (staged in shared memory) in lock step.
+// a13-a15).
+//
+// Per step (render-prepare node, inside the step graph; role of the reference's
+// instanceTransformUpdate / viewTransformUpdate / lightUpdate / mortonCodeUpdate /
+// three archetype sorts / bvhBuildFast / bvhConstructAABBs / bvhWidenTree /
+// exportCountsGPU: src/render/ecs_system.cpp:100-348, 486-597 and
+// src/mw/device/bvh.cpp:731-1217):
+//   renderGatherInstancesKernel  every world's renderable instances -> InstanceData +
+//                                world box (mesh root box under TRS)
+//   renderLightKernels           carriers refresh their LightDesc, lights gathered per world
+//   renderGatherViewsKernel      PerspectiveCameraData per view
+//   renderBuildTLASKernel        ONE WARP PER WORLD, all in shared memory: 30-bit Morton
+//                                codes of the box centres inside the world's bounds, rank
+//                                sort, Karras' parallel LBVH, bottom-up boxes, collapse to
+//                                4-wide nodes, quantise -> QBVHNode[] (the reference's
+//                                traversal format)
+// Render graph: renderRaycastKernel, one thread per pixel, one block per view
+// (8 x 4 pixel tiles per warp): TLAS -> instance -> object-space ray -> BLAS
+// (reference-format MeshBVH: quantised 4-wide nodes over de-indexed triangles)
+// -> watertight ray / triangle test; materials (override colour / material
+// table), lights with shadow rays, RGBA8 + f32 depth.
 //
 // Image formation follows the reference's CUDA ray tracer
-// (src/mw/device/bvh_raycast.cpp): ray generation :58-88, object-space ray
-// and t rescaling :620-645 / :744-751, watertight ray-triangle test :317-448
-// (explicit fmaf kept), depth / RGBA8 output :820-838, 940-1029, unlit colour
-// = max(0.2, 0) * colour with zero lights :848-938.  The acceleration structure
-// is different by design: the reference sorts render entities by Morton code
-// three times per step and builds a per-world LBVH + 4-wide quantised QBVH
-// (src/mw/device/bvh.cpp); with tens of instances per world a linear,
-// branch-coherent scan of world boxes beats a divergent tree walk, and a hit's
-// depth does not depend on the structure that found it.  (Meshes here are flat
-// triangle ranges; a mesh BLAS builder is SURVEY 8f N4.)
+// (src/mw/device/bvh_raycast.cpp): ray generation :58-88, object-space ray and
+// t rescaling :620-645 / :744-751, watertight ray-triangle test :317-448
+// (explicit fmaf kept), colour / normal of a hit :756-815, lighting :848-938,
+// depth / RGBA8 output :820-838, 940-1029.  How the structures are built and
+// walked is this engine's own (the reference builds the TLAS with ~10 megakernel
+// nodes and global atomics and walks it with a packed-group traversal); a
+// closest hit does not depend on the tree that found it.
 //
-// Parity: the reference can only render on its GPU backend (CPU backend forces
-// raycast off, src/render/ecs_system.cpp:684-689), so there is no reference
-// output to compare with here -- "parity unpinned"; tests compare against the
-// numpy restatement oracle/restate_render.py of the same formulas.
+// Parity: the reference can only render on its GPU backend (the CPU backend
+// forces the ray caster off, src/render/ecs_system.cpp:684-689), so there is no
+// reference image to compare with -- "parity unpinned".  tests/test_render_bvh.py
+// pins every pixel's (instance, triangle, depth) to a brute-force float64
+// closest hit over ALL triangles of the world; tests/test_render.py keeps the
+// numpy restatement of the image-formation formulas.
 #include "physics_host.hpp"
 #include "render_state.h"
 
 #include <madrona/math.hpp>
 #include <cfloat>
 #include <algorithm>
+#include <vector>
 
 namespace mb2 {
 
@@ -41,6 +57,7 @@ struct RenderHost {
     RenderState *dRender = nullptr;
     RenderState hRender;
     bool active = false;
+    size_t tlasSmem = 0;
 };
 
 struct RenderCameraComp {     // == madrona::render::RenderCamera
@@ -49,8 +66,6 @@ struct RenderCameraComp {     // == madrona::render::RenderCamera
     float zNear;
     Vector3 cameraOffset;
 };
-
-constexpr int kStagedInstances = 64;
 
 // ---- render-prepare: instances ---------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -89,12 +104,17 @@ renderGatherInstancesKernel(EngineState *Sp)
                     inst.rotation = RQuat { q.w, q.x, q.y, q.z };
                     inst.scale = RVec3 { s.d0, s.d1, s.d2 };
                     inst.objectID = ((const i32 *)t.columns[ra.cols[RCObjectID]])[row];
+                    // instanceTransformUpdate (no material components: mesh default) /
+                    // instanceTransformUpdateWithMat (ecs_system.cpp:100-159, 211-250); a
+                    // ColorOverride without a MaterialOverride means "use this colour"
                     inst.color = ra.colorCol >= 0 ? ((const u32 *)t.columns[ra.colorCol])[row] : 0xFFFFFFu;
+                    inst.matID = ra.matCol >= 0 ? ((const i32 *)t.columns[ra.matCol])[row]
+                                                : (ra.colorCol >= 0 ? -2 : -1);
                     AABB box { { 0, 0, 0 }, { 0, 0, 0 } };
                     if (inst.objectID >= 0 && (u32)inst.objectID < R.numMeshes) {
-                        const MeshDesc &m = R.meshes[inst.objectID];
-                        box = AABB { { m.aabbMin[0], m.aabbMin[1], m.aabbMin[2] },
-                                     { m.aabbMax[0], m.aabbMax[1], m.aabbMax[2] } }.applyTRS(p, q, s);
+                        const MeshBVH &m = R.meshes[inst.objectID];
+                        box = AABB { { m.rootAABBMin[0], m.rootAABBMin[1], m.rootAABBMin[2] },
+                                     { m.rootAABBMax[0], m.rootAABBMax[1], m.rootAABBMax[2] } }.applyTRS(p, q, s);
                     }
                     inst.aabbMin[0] = box.pMin.x; inst.aabbMin[1] = box.pMin.y; inst.aabbMin[2] = box.pMin.z;
                     inst.aabbMax[0] = box.pMax.x; inst.aabbMax[1] = box.pMax.y; inst.aabbMax[2] = box.pMax.z;
@@ -110,6 +130,73 @@ renderGatherInstancesKernel(EngineState *Sp)
             running = R.maxInstancesPerWorld;
         }
         R.instanceCounts[w] = running;
+        atomicAdd(&R.totalNumInstances, (u32)running);
+    }
+}
+
+// ---- render-prepare: lights -------------------------------------------------------------
+// lightUpdate (ecs_system.cpp:183-209): every light carrier writes its current
+// description into its light entity; then each world's LightDescs are listed.
+__global__ void __launch_bounds__(256)
+renderLightUpdateKernel(EngineState *Sp, u32 archetype, i32 carrier_col, i32 pos_col, i32 dir_col, i32 type_col,
+                        i32 shadow_col, i32 cutoff_col, i32 intensity_col, i32 active_col)
+{
+    pdlSync();
+    EngineState &S = *Sp;
+    const RenderState &R = *S.render;
+    const TableDesc &t = S.tables[archetype];
+    const i32 n = t.numRows;
+    for (i32 row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        if (((const i32 *)t.columns[1])[row] < 0) continue;
+        const u64 packed = ((const u64 *)t.columns[carrier_col])[row];
+        const i32 id = (i32)(u32)(packed >> 32);
+        const u32 gen = (u32)(packed & 0xFFFFFFFFull);
+        if (id < 0 || id >= S.entityCapacity) continue;
+        const EntitySlot slot = S.entitySlots[id];
+        if (slot.gen != gen || (u32)slot.a != R.lightArchetype) continue;
+        LightDescComp &d = ((LightDescComp *)S.tables[R.lightArchetype].columns[R.lightCol])[slot.b];
+        const Vector3 p = ((const Vector3 *)t.columns[pos_col])[row];
+        const Vector3 dir = ((const Vector3 *)t.columns[dir_col])[row];
+        d.type = ((const unsigned char *)t.columns[type_col])[row];
+        d.castShadow = ((const unsigned char *)t.columns[shadow_col])[row];
+        d.position[0] = p.x; d.position[1] = p.y; d.position[2] = p.z;
+        d.direction[0] = dir.x; d.direction[1] = dir.y; d.direction[2] = dir.z;
+        d.cutoff = ((const float *)t.columns[cutoff_col])[row];
+        d.intensity = ((const float *)t.columns[intensity_col])[row];
+        d.active = ((const unsigned char *)t.columns[active_col])[row];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+renderGatherLightsKernel(EngineState *Sp)
+{
+    pdlSync();
+    EngineState &S = *Sp;
+    RenderState &R = *S.render;
+    const TableDesc &t = S.tables[R.lightArchetype];
+    const i32 W = (i32)S.numWorlds;
+    for (i32 w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+        const i32 first = t.worldOffsets[w];
+        const i32 count = t.worldCounts[w];
+        i32 kept = 0;
+        for (i32 r = first; r < first + count && kept < kMaxLightsPerWorld; r++) {
+            if (((const i32 *)t.columns[1])[r] != w) continue;
+            const LightDescComp d = ((const LightDescComp *)t.columns[R.lightCol])[r];
+            RenderLight l;
+            l.directional = d.type ? 1u : 0u;
+            l.castShadow = d.castShadow ? 1u : 0u;
+            l.position = RVec3 { d.position[0], d.position[1], d.position[2] };
+            l.direction = RVec3 { d.direction[0], d.direction[1], d.direction[2] };
+            l.cutoff = d.cutoff;
+            l.intensity = d.intensity;
+            l.active = d.active ? 1u : 0u;
+            R.lights[(size_t)w * kMaxLightsPerWorld + kept++] = l;
+        }
+        R.lightCounts[w] = kept;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // exportCountsGPU (ecs_system.cpp:317-348)
+        R.totalNumViews = (u32)S.tables[R.outputArchetype].numRows;
     }
 }
 
@@ -149,8 +236,6 @@ renderGatherViewsKernel(EngineState *Sp)
         R.views[out_row] = v;
     }
 }
-
-// ---- ray casting ------------------------------------------------------------------------------
 
 struct RayShear {
     int kx, ky, kz;
@@ -218,69 +303,402 @@ __device__ __forceinline__ bool rayTriangle(Vector3 a, Vector3 b, Vector3 c, con
     return true;
 }
 
-// The same test on triangles that were already translated by the (per view, per
-// instance) ray origin and staged in shared memory, with the axis permutation
-// resolved at compile time: rays of a warp mostly share their dominant axis,
-// and the run-time component selects were the single largest cost of the
-// generic version (ncu, profiles/r01_ncu_raycast.csv).  Same operations on the
-// same operands as rayTriangle -> same bits.
-template <int KZ, bool FLIP>
-__device__ __forceinline__ void stagedTriangles(const float *tris, const u32 num_tris, const float Sx,
-                                                const float Sy, const float Sz, float &t_obj, bool &hit,
-                                                Vector3 &n_obj)
+// ---- render-prepare: per-world TLAS ----------------------------------------------------------
+// One warp per world; everything lives in the warp's slice of dynamic shared
+// memory until the 4-wide nodes are written out.
+struct TLASScratch {
+    unsigned long long *keys;     // [n] morton << 32 | gather index
+    float *leafBox;               // [n][6] in SORTED order
+    float *nodeBox;               // [n - 1][6] binary internal nodes
+    short *left, *right;          // [n - 1] child: >= 0 internal, < 0: ~leaf (sorted position)
+    short *parent;                // [2n - 1]: internal nodes first, then leaves
+    int *flags;                   // [n - 1] arrival counters of the bottom-up pass
+    short *wideBin;               // [n] binary node of each wide node
+    int *order;                   // [n] sorted position -> gather index
+};
+
+__host__ __device__ inline size_t tlasScratchBytes(int n)
 {
-    constexpr int K1 = (KZ + 1) % 3, K2 = (KZ + 2) % 3;
-    constexpr int KX = FLIP ? K2 : K1, KY = FLIP ? K1 : K2;
-    for (u32 tri = 0; tri < num_tris; tri++) {
-        const float *t9 = tris + tri * 9;
-        const float a_kz = t9[KZ], a_kx = t9[KX], a_ky = t9[KY];
-        const float b_kz = t9[3 + KZ], b_kx = t9[3 + KX], b_ky = t9[3 + KY];
-        const float c_kz = t9[6 + KZ], c_kx = t9[6 + KX], c_ky = t9[6 + KY];
-
-        const float Ax = fmaf(-Sx, a_kz, a_kx), Ay = fmaf(-Sy, a_kz, a_ky);
-        const float Bx = fmaf(-Sx, b_kz, b_kx), By = fmaf(-Sy, b_kz, b_ky);
-        const float Cx = fmaf(-Sx, c_kz, c_kx), Cy = fmaf(-Sy, c_kz, c_ky);
-
-        float U = fmaf(Cx, By, -Cy * Bx);
-        float V = fmaf(Ax, Cy, -Ay * Cx);
-        float W = fmaf(Bx, Ay, -By * Ax);
-
-        constexpr float eps = 1e-7;
-        if (U > -eps && U < eps) U = 0.f;
-        if (V > -eps && V < eps) V = 0.f;
-        if (W > -eps && W < eps) W = 0.f;
-
-        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
-
-        if (U == 0.0f || V == 0.0f || W == 0.0f) {
-            U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
-            V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
-            W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
-            if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) continue;
-        }
-
-        const float det = U + V + W;
-        if (det == 0.f) continue;
-
-        const float Az = Sz * a_kz, Bz = Sz * b_kz, Cz = Sz * c_kz;
-        const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
-
-        const u32 sign = __float_as_uint(det) & 0x80000000u;
-        const float xor_T = __uint_as_float(__float_as_uint(T) ^ sign);
-        const float abs_det = copysignf(det, 1.f);
-        if (xor_T < 0.0f || xor_T > t_obj * abs_det) continue;
-
-        const float rcp = 1.0f / det;
-        t_obj = T * rcp;
-        hit = true;
-        const Vector3 A { t9[0], t9[1], t9[2] }, B { t9[3], t9[4], t9[5] }, C { t9[6], t9[7], t9[8] };
-        n_obj = madrona::math::normalize(cross(B - A, C - A));
-    }
+    return (size_t)n * (8 + 24 + 24 + 2 + 2 + 4 + 4 + 2 + 4) + 64;
 }
 
-constexpr int kTriArena = 640;      // origin-relative triangles staged per block (23 KB)
+__device__ __forceinline__ u32 expandBits10(u32 v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
 
-__global__ void __launch_bounds__(256, 4)
+__device__ __forceinline__ int commonPrefix(const unsigned long long *keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    return __clzll((long long)(keys[i] ^ keys[j]));     // keys are unique (index in the low word)
+}
+
+__global__ void __launch_bounds__(32)
+renderBuildTLASKernel(EngineState *Sp)
+{
+    pdlSync();
+    extern __shared__ __align__(16) unsigned char tlas_smem[];
+    EngineState &S = *Sp;
+    RenderState &R = *S.render;
+    const int lane = threadIdx.x;
+    const i32 w = (i32)blockIdx.x;
+    const i32 n = R.instanceCounts[w];
+    const RenderInstance *inst = R.instances + (size_t)w * R.maxInstancesPerWorld;
+    QBVHNode *out = R.tlasNodes + (size_t)w * R.maxInstancesPerWorld;
+    if (n <= 0) {
+        if (lane == 0) R.tlasNodeCounts[w] = 0;
+        return;
+    }
+    const int cap = R.maxInstancesPerWorld;
+    TLASScratch sc;
+    {
+        unsigned char *p = tlas_smem;
+        sc.keys = (unsigned long long *)p; p += (size_t)cap * 8;
+        sc.leafBox = (float *)p; p += (size_t)cap * 24;
+        sc.nodeBox = (float *)p; p += (size_t)cap * 24;
+        sc.flags = (int *)p; p += (size_t)cap * 4;
+        sc.order = (int *)p; p += (size_t)cap * 4;
+        sc.left = (short *)p; p += (size_t)cap * 2;
+        sc.right = (short *)p; p += (size_t)cap * 2;
+        sc.parent = (short *)p; p += (size_t)cap * 4;
+        sc.wideBin = (short *)p;
+    }
+
+    // 1. world bounds of the box centres, Morton keys
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int i = lane; i < n; i += 32) {
+        for (int a = 0; a < 3; a++) {
+            const float c = 0.5f * (inst[i].aabbMin[a] + inst[i].aabbMax[a]);
+            lo[a] = fminf(lo[a], c);
+            hi[a] = fmaxf(hi[a], c);
+        }
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+        for (int a = 0; a < 3; a++) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    for (int i = lane; i < n; i += 32) {
+        u32 code = 0;
+        for (int a = 0; a < 3; a++) {
+            const float c = 0.5f * (inst[i].aabbMin[a] + inst[i].aabbMax[a]);
+            const float ext = hi[a] - lo[a];
+            float u = ext > 0.f ? (c - lo[a]) / ext : 0.f;
+            u = fminf(fmaxf(u * 1024.f, 0.f), 1023.f);
+            code |= expandBits10((u32)u) << a;
+        }
+        sc.keys[i] = ((unsigned long long)code << 32) | (u32)i;
+    }
+    __syncwarp();
+
+    // 2. rank sort (n is tens to a few hundred): sorted position of every instance
+    for (int i = lane; i < n; i += 32) {
+        const unsigned long long mine = sc.keys[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) rank += sc.keys[j] < mine ? 1 : 0;
+        sc.order[rank] = i;
+    }
+    __syncwarp();
+    // keys / boxes in sorted order (keys rewritten in place through registers)
+    {
+        unsigned long long mine[16];
+        const int per = (n + 31) / 32;
+        for (int k = 0; k < per && k < 16; k++) {
+            const int pos = lane + 32 * k;
+            mine[k] = pos < n ? sc.keys[sc.order[pos]] : 0ull;
+        }
+        __syncwarp();
+        for (int k = 0; k < per && k < 16; k++) {
+            const int pos = lane + 32 * k;
+            if (pos < n) {
+                sc.keys[pos] = mine[k];
+                const RenderInstance &ri = inst[sc.order[pos]];
+                for (int a = 0; a < 3; a++) {
+                    sc.leafBox[pos * 6 + a] = ri.aabbMin[a];
+                    sc.leafBox[pos * 6 + 3 + a] = ri.aabbMax[a];
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    if (n == 1) {
+        if (lane == 0) {
+            float cmin[kBVHWidth][3], cmax[kBVHWidth][3];
+            for (int a = 0; a < 3; a++) {
+                cmin[0][a] = sc.leafBox[a];
+                cmax[0][a] = sc.leafBox[3 + a];
+            }
+            QBVHNode node;
+            quantizeNode(node, 1, cmin, cmax);
+            node.childrenIdx[0] = 0x80000000u | (u32)sc.order[0];
+            node.triSize[0] = 0;
+            out[0] = node;
+            R.tlasNodeCounts[w] = 1;
+        }
+        return;
+    }
+
+    // 3. Karras 2012: internal node i covers a key range; leaves are sorted positions
+    for (int i = lane; i < n - 1; i += 32) {
+        const int d = commonPrefix(sc.keys, n, i, i + 1) - commonPrefix(sc.keys, n, i, i - 1) >= 0 ? 1 : -1;
+        const int delta_min = commonPrefix(sc.keys, n, i, i - d);
+        int lmax = 2;
+        while (commonPrefix(sc.keys, n, i, i + lmax * d) > delta_min) lmax <<= 1;
+        int l = 0;
+        for (int t = lmax >> 1; t >= 1; t >>= 1) {
+            if (commonPrefix(sc.keys, n, i, i + (l + t) * d) > delta_min) l += t;
+        }
+        const int j = i + l * d;
+        const int delta_node = commonPrefix(sc.keys, n, i, j);
+        int s = 0;
+        for (int t = (l + 1) >> 1; ; t = (t + 1) >> 1) {
+            if (commonPrefix(sc.keys, n, i, i + (s + t) * d) > delta_node) s += t;
+            if (t == 1) break;
+        }
+        const int gamma = i + s * d + min(d, 0);
+        const int first = min(i, j), last = max(i, j);
+        const int lc = first == gamma ? ~gamma : gamma;             // leaf: ~position
+        const int rc = last == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+        sc.left[i] = (short)lc;
+        sc.right[i] = (short)rc;
+        sc.parent[lc >= 0 ? lc : (n - 1) + (~lc)] = (short)i;
+        sc.parent[rc >= 0 ? rc : (n - 1) + (~rc)] = (short)i;
+        sc.flags[i] = 0;
+    }
+    if (lane == 0) sc.parent[0] = -1;
+    __syncwarp();
+
+    // 4. boxes, bottom-up: the second thread to reach a node owns it
+    for (int leaf = lane; leaf < n; leaf += 32) {
+        int node = sc.parent[(n - 1) + leaf];
+        while (node >= 0) {
+            __threadfence_block();
+            if (atomicAdd(&sc.flags[node], 1) == 0) break;
+            const int lc = sc.left[node], rc = sc.right[node];
+            const float *lb = lc >= 0 ? sc.nodeBox + lc * 6 : sc.leafBox + (~lc) * 6;
+            const float *rb = rc >= 0 ? sc.nodeBox + rc * 6 : sc.leafBox + (~rc) * 6;
+            for (int a = 0; a < 3; a++) {
+                sc.nodeBox[node * 6 + a] = fminf(lb[a], rb[a]);
+                sc.nodeBox[node * 6 + 3 + a] = fmaxf(lb[3 + a], rb[3 + a]);
+            }
+            node = sc.parent[node];
+        }
+    }
+    __syncwarp();
+
+    // 5. collapse to 4-wide nodes, breadth first; flags[0] now counts wide nodes
+    if (lane == 0) {
+        sc.wideBin[0] = 0;
+        sc.flags[0] = 1;
+    }
+    __syncwarp();
+    // waves: nodes [done, count) exist and are not written yet; writing them appends
+    // their inner children behind `count`
+    for (int done = 0;;) {
+        const int count_now = *(volatile int *)&sc.flags[0];
+        if (done >= count_now) break;
+        const int k = done + lane;
+        __syncwarp();
+        if (k < count_now) {
+            const int bin = sc.wideBin[k];
+            int kids[kBVHWidth];
+            int nk = 2;
+            kids[0] = sc.left[bin];
+            kids[1] = sc.right[bin];
+            while (nk < kBVHWidth) {
+                int pick = -1;
+                float best = -1.f;
+                for (int c = 0; c < nk; c++) {
+                    if (kids[c] < 0) continue;
+                    const float *b = sc.nodeBox + kids[c] * 6;
+                    const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+                    const float area = dx * dy + dy * dz + dz * dx;
+                    if (area > best) {
+                        best = area;
+                        pick = c;
+                    }
+                }
+                if (pick < 0) break;
+                const int inner = kids[pick];
+                kids[pick] = sc.left[inner];
+                kids[nk++] = sc.right[inner];
+            }
+            float cmin[kBVHWidth][3], cmax[kBVHWidth][3];
+            for (int c = 0; c < nk; c++) {
+                const float *b = kids[c] >= 0 ? sc.nodeBox + kids[c] * 6 : sc.leafBox + (~kids[c]) * 6;
+                for (int a = 0; a < 3; a++) {
+                    cmin[c][a] = b[a];
+                    cmax[c][a] = b[3 + a];
+                }
+            }
+            QBVHNode node;
+            quantizeNode(node, nk, cmin, cmax);
+            for (int c = 0; c < nk; c++) {
+                node.triSize[c] = 0;
+                if (kids[c] < 0) {
+                    node.childrenIdx[c] = 0x80000000u | (u32)sc.order[~kids[c]];
+                } else {
+                    const int id = atomicAdd(&sc.flags[0], 1);
+                    sc.wideBin[id] = (short)kids[c];
+                    node.childrenIdx[c] = (u32)id;
+                }
+            }
+            out[k] = node;
+        }
+        __syncwarp();
+        done = min(done + 32, count_now);
+    }
+    if (lane == 0) R.tlasNodeCounts[w] = sc.flags[0];
+}
+
+// ---- ray casting ------------------------------------------------------------------------------
+
+struct RayHit {
+    float t;
+    Vector3 normalObj;      // object-space geometric normal of the hit triangle
+    int instance;           // gather index inside the world, -1: miss
+    int triangle;           // triangle index inside the instance's mesh
+};
+
+// child boxes of a quantised node against the ray (mesh_bvh.inl:100-160): the slab
+// planes are evaluated straight in the node's quantised frame
+struct NodeRay {
+    float dirX, dirY, dirZ;     // 2^exp / d
+    float orgX, orgY, orgZ;     // (minPoint - o) / d
+};
+
+__device__ __forceinline__ NodeRay nodeRay(const QBVHNode &node, Vector3 o, Vector3 d)
+{
+    constexpr float diveps = 0.0000001f;
+    const float ix = copysignf(d.x == 0 ? 1 / diveps : 1 / d.x, d.x);
+    const float iy = copysignf(d.y == 0 ? 1 / diveps : 1 / d.y, d.y);
+    const float iz = copysignf(d.z == 0 ? 1 / diveps : 1 / d.z, d.z);
+    NodeRay r;
+    r.dirX = __uint_as_float((u32)(node.expX + 127) << 23) * ix;
+    r.dirY = __uint_as_float((u32)(node.expY + 127) << 23) * iy;
+    r.dirZ = __uint_as_float((u32)(node.expZ + 127) << 23) * iz;
+    r.orgX = (node.minPoint[0] - o.x) * ix;
+    r.orgY = (node.minPoint[1] - o.y) * iy;
+    r.orgZ = (node.minPoint[2] - o.z) * iz;
+    return r;
+}
+
+__device__ __forceinline__ bool childHit(const QBVHNode &node, const NodeRay &r, int i, float t_max)
+{
+    const float nx = node.qMinX[i] * r.dirX + r.orgX, fx = node.qMaxX[i] * r.dirX + r.orgX;
+    const float ny = node.qMinY[i] * r.dirY + r.orgY, fy = node.qMaxY[i] * r.dirY + r.orgY;
+    const float nz = node.qMinZ[i] * r.dirZ + r.orgZ, fz = node.qMaxZ[i] * r.dirZ + r.orgZ;
+    const float t_near = fmaxf(fminf(nx, fx), fmaxf(fminf(ny, fy), fmaxf(fminf(nz, fz), 0.f)));
+    const float t_far = fminf(fmaxf(nx, fx), fminf(fmaxf(ny, fy), fminf(fmaxf(nz, fz), t_max)));
+    return t_near <= t_far;
+}
+
+constexpr int kTraceStack = 48;
+
+// Closest hit (ANY_HIT: first hit) of a world-space ray against one world.
+template <bool ANY_HIT>
+__device__ RayHit traceWorld(const RenderState &R, const QBVHNode *tlas, const i32 tlas_nodes,
+                             const RenderInstance *instances, Vector3 o, Vector3 d, float t_min, float t_max,
+                             int *stack)
+{
+    RayHit hit { t_max, Vector3 { 0, 0, 0 }, -1, -1 };
+    if (tlas_nodes <= 0) return hit;
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const QBVHNode &node = tlas[stack[--sp]];
+        const NodeRay nr = nodeRay(node, o, d);
+#pragma unroll
+        for (int c = 0; c < kBVHWidth; c++) {
+            const u32 child = node.childrenIdx[c];
+            if (child == 0xFFFFFFFFu) continue;
+            if (!childHit(node, nr, c, hit.t)) continue;
+            if (!(child & 0x80000000u)) {
+                if (sp < kTraceStack) stack[sp++] = (int)child;
+                continue;
+            }
+            // ---- an instance: object-space ray; t is rescaled by |d'| while inside the mesh
+            const int ii = (int)(child & 0x7FFFFFFFu);
+            const RenderInstance &inst = instances[ii];
+            if (inst.scale.x == 0.f || inst.scale.y == 0.f || inst.scale.z == 0.f || inst.objectID < 0 ||
+                    (u32)inst.objectID >= R.numMeshes) {
+                continue;
+            }
+            const MeshBVH &mesh = R.meshes[inst.objectID];
+            const Quat q { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
+            const Diag3x3 inv_scale = Diag3x3 { inst.scale.x, inst.scale.y, inst.scale.z }.inv();
+            const Vector3 p { inst.position.x, inst.position.y, inst.position.z };
+            const Vector3 oo = inv_scale * q.inv().rotateVec(o - p);
+            Vector3 od = inv_scale * q.inv().rotateVec(d);
+            const float t_scale = od.length();
+            od /= t_scale;
+            float t_obj = hit.t * t_scale;
+            const float t_obj_min = t_min * t_scale;
+            const Diag3x3 inv_od = Diag3x3::fromVec(od).inv();
+            const RayShear rs = rayShear(od, inv_od);
+
+            bool hit_here = false;
+            Vector3 n_obj { 0, 0, 0 };
+            int tri_here = -1;
+            const int blas_base = sp;
+            if (sp < kTraceStack) stack[sp++] = 0;
+            while (sp > blas_base) {
+                const QBVHNode &bn = mesh.nodes[stack[--sp]];
+                const NodeRay br = nodeRay(bn, oo, od);
+#pragma unroll
+                for (int bc = 0; bc < kBVHWidth; bc++) {
+                    const u32 bchild = bn.childrenIdx[bc];
+                    if (bchild == 0xFFFFFFFFu) continue;
+                    if (!childHit(bn, br, bc, t_obj)) continue;
+                    if (!(bchild & 0x80000000u)) {
+                        if (sp < kTraceStack) stack[sp++] = (int)bchild;
+                        continue;
+                    }
+                    const u32 first_tri = bchild & 0x7FFFFFFFu;
+                    for (u32 k = 0; k < bn.triSize[bc]; k++) {
+                        const BVHVertex *v = mesh.vertices + (size_t)(first_tri + k) * 3;
+                        const Vector3 a { v[0].pos[0], v[0].pos[1], v[0].pos[2] };
+                        const Vector3 b { v[1].pos[0], v[1].pos[1], v[1].pos[2] };
+                        const Vector3 cc { v[2].pos[0], v[2].pos[1], v[2].pos[2] };
+                        float t;
+                        Vector3 nn;
+                        if (rayTriangle(a, b, cc, rs, oo, t_obj, &t, &nn) && t >= t_obj_min) {
+                            t_obj = t;
+                            hit_here = true;
+                            n_obj = nn;
+                            tri_here = (int)(first_tri + k);
+                        }
+                    }
+                }
+                if (ANY_HIT && hit_here) {
+                    sp = blas_base;
+                    break;
+                }
+            }
+            if (hit_here) {
+                hit.t = t_obj / t_scale;
+                hit.normalObj = n_obj;
+                hit.instance = ii;
+                hit.triangle = tri_here;
+                if (ANY_HIT) return hit;
+            }
+        }
+    }
+    return hit;
+}
+
+__device__ __forceinline__ Vector3 hexToRgb(u32 hex)
+{
+    return Vector3 { ((hex >> 16) & 0xFF) / 255.0f, ((hex >> 8) & 0xFF) / 255.0f, (hex & 0xFF) / 255.0f };
+}
+
+__global__ void __launch_bounds__(256, 3)
 renderRaycastKernel(EngineState *Sp)
 {
     pdlSync();
@@ -289,27 +707,21 @@ renderRaycastKernel(EngineState *Sp)
     const TableDesc &out_tbl = S.tables[R.outputArchetype];
     const i32 num_views = min(out_tbl.numRows, R.maxViews);
     const u32 res = R.resolution;
-    // One block traces a whole view (the per-view staging below is paid once);
-    // a warp traces 8 x 4 pixel tiles: coherent rays (same instances entered,
-    // same dominant axis) instead of 32-pixel row segments.
+    // One block traces a whole view; a warp traces 8 x 4 pixel tiles: coherent
+    // rays (same nodes entered, same dominant axis) instead of 32-pixel row segments.
     const u32 tiles_x = (res + 7) / 8;
     const u32 num_tiles = tiles_x * ((res + 3) / 4);
     const size_t bytes_per_view = (size_t)res * res * 4;
-
-    __shared__ RenderInstance staged[kStagedInstances];
-    __shared__ RenderInstance stage_tmp[kStagedInstances];
-    __shared__ float stage_key[kStagedInstances];
-    __shared__ int stage_count[2];
-    __shared__ float inst_origin[kStagedInstances][3];   // ray origin in the instance's object space
-    __shared__ int inst_tris[kStagedInstances];          // arena offset, -1: not staged, -2: skip instance
-    __shared__ int inst_nt[kStagedInstances];            // triangles of the instance's mesh
-    __shared__ int arena_used;
-    __shared__ float tri_arena[kTriArena * 9];
+    int stack[kTraceStack];
 
     for (i32 v = blockIdx.y; v < num_views; v += gridDim.y) {
         const RenderView view = R.views[v];
         const i32 w = view.worldIDX;
-        const i32 world_inst = min(R.instanceCounts[w], kStagedInstances);
+        const QBVHNode *tlas = R.tlasNodes + (size_t)w * R.maxInstancesPerWorld;
+        const i32 tlas_nodes = R.tlasNodeCounts[w];
+        const RenderInstance *instances = R.instances + (size_t)w * R.maxInstancesPerWorld;
+        const RenderLight *lights = R.lights + (size_t)w * kMaxLightsPerWorld;
+        const i32 num_lights = R.lightCounts[w];
 
         // camera frame (shared by every pixel of the view)
         const Quat rot { view.rotation.w, view.rotation.x, view.rotation.y, view.rotation.z };
@@ -321,198 +733,91 @@ renderRaycastKernel(EngineState *Sp)
         const Vector3 u = rot.inv().rotateVec({ 1, 0, 0 });
         const Vector3 vv = cross(forward, u).normalize();
 
-        // Stage the world's instances, keeping (in order) only those whose box
-        // touches the view frustum: no ray of this view could pass their slab
-        // test, so dropping them changes nothing but the work per ray.
-        __syncthreads();
-        if (threadIdx.x < 64) {
-            const int k = threadIdx.x;
-            bool keep = false;
-            RenderInstance inst;
-            if (k < world_inst) {
-                inst = R.instances[(size_t)w * R.maxInstancesPerWorld + k];
-                keep = true;
-                const float hm = fabsf(h) * 1.02f + 0.01f;     // widened: conservative
-                const Vector3 normals[4] = { forward * hm - u, forward * hm + u,
-                                             forward * hm - vv, forward * hm + vv };
-                for (int pl = 0; pl < 4; pl++) {
-                    const Vector3 n = normals[pl];
-                    // box corner furthest along n
-                    const Vector3 far_corner {
-                        n.x >= 0 ? inst.aabbMax[0] : inst.aabbMin[0],
-                        n.y >= 0 ? inst.aabbMax[1] : inst.aabbMin[1],
-                        n.z >= 0 ? inst.aabbMax[2] : inst.aabbMin[2] };
-                    if (dot(far_corner - ray_start, n) < 0.f) keep = false;
-                }
-            }
-            const u32 kept = __ballot_sync(0xffffffffu, keep);
-            if (threadIdx.x == 0) stage_count[0] = __popc(kept);
-            if (threadIdx.x == 32) stage_count[1] = __popc(kept);
-            // near-to-far key: squared distance from the eye to the instance's box
-            // (0 inside).  Visiting near instances first shrinks t_max early, so
-            // the boxes of far instances fail their slab test instead of being
-            // entered.  Culled instances sort to the end.
-            float key = FLT_MAX;
-            if (keep) {
-                const float dx = fmaxf(fmaxf(inst.aabbMin[0] - ray_start.x, 0.f), ray_start.x - inst.aabbMax[0]);
-                const float dy = fmaxf(fmaxf(inst.aabbMin[1] - ray_start.y, 0.f), ray_start.y - inst.aabbMax[1]);
-                const float dz = fmaxf(fmaxf(inst.aabbMin[2] - ray_start.z, 0.f), ray_start.z - inst.aabbMax[2]);
-                key = dx * dx + dy * dy + dz * dz;
-            }
-            stage_key[k] = key;
-            stage_tmp[k] = inst;
-        }
-        __syncthreads();
-        if (threadIdx.x < 64) {
-            // rank sort, ties broken by the original (engine) order
-            const int k = threadIdx.x;
-            const float mine = stage_key[k];
-            int rank = 0;
-            for (int j = 0; j < 64; j++) {
-                const float other = stage_key[j];
-                rank += (other < mine || (other == mine && j < k)) ? 1 : 0;
-            }
-            if (mine != FLT_MAX) staged[rank] = stage_tmp[k];
-        }
-        __syncthreads();
-        const i32 num_inst = stage_count[0] + stage_count[1];
-
-        // Per (view, instance) work, hoisted out of the per-ray loop: the ray
-        // origin in object space and the mesh's triangles relative to it.
-        if (threadIdx.x < 64 && threadIdx.x < num_inst) {
-            const int k = threadIdx.x;
-            const RenderInstance &inst = staged[k];
-            int slot = -1;
-            if (inst.scale.x == 0.f || inst.scale.y == 0.f || inst.scale.z == 0.f ||
-                    inst.objectID < 0 || (u32)inst.objectID >= R.numMeshes) {
-                slot = -2;
-            } else {
-                const Quat q { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
-                const Diag3x3 inv_scale = Diag3x3 { inst.scale.x, inst.scale.y, inst.scale.z }.inv();
-                const Vector3 p { inst.position.x, inst.position.y, inst.position.z };
-                const Vector3 o = inv_scale * q.inv().rotateVec(ray_start - p);
-                inst_origin[k][0] = o.x; inst_origin[k][1] = o.y; inst_origin[k][2] = o.z;
-            }
-            inst_tris[k] = slot;
-            inst_nt[k] = slot == -2 ? 0 : (int)R.meshes[inst.objectID].numTriangles;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int used = 0;
-            for (int k = 0; k < num_inst; k++) {
-                if (inst_tris[k] == -2) continue;
-                if (used + inst_nt[k] <= kTriArena) {
-                    inst_tris[k] = used;
-                    used += inst_nt[k];
-                }
-            }
-            arena_used = used;
-        }
-        __syncthreads();
-        // all staged triangle corners in one flat pass (arena slot -> owning instance by scan)
-        for (int e = threadIdx.x; e < arena_used * 3; e += blockDim.x) {
-            const int tri_slot = e / 3;
-            int k = 0;
-            for (int j = 0; j < num_inst; j++) {
-                if (inst_tris[j] >= 0 && inst_tris[j] <= tri_slot) k = j;
-            }
-            const MeshDesc &mesh = R.meshes[staged[k].objectID];
-            const u32 i = (u32)(e - inst_tris[k] * 3);
-            const u32 vi = R.indices[(size_t)mesh.firstTriangle * 3 + i];
-            const Vector3 vert { R.vertices[vi * 3], R.vertices[vi * 3 + 1], R.vertices[vi * 3 + 2] };
-            const Vector3 rel = vert - Vector3 { inst_origin[k][0], inst_origin[k][1], inst_origin[k][2] };
-            float *dst = tri_arena + (size_t)e * 3;
-            dst[0] = rel.x; dst[1] = rel.y; dst[2] = rel.z;
-        }
-        __syncthreads();
-
         for (u32 tile = threadIdx.x >> 5; tile < num_tiles; tile += blockDim.x >> 5) {
-        const u32 px = (tile % tiles_x) * 8 + (threadIdx.x & 7);
-        const u32 py = (tile / tiles_x) * 4 + ((threadIdx.x & 31) >> 3);
-        const bool in_image = px < res && py < res;
-        if (!in_image) continue;
+            const u32 px = (tile % tiles_x) * 8 + (threadIdx.x & 7);
+            const u32 py = (tile / tiles_x) * 4 + ((threadIdx.x & 31) >> 3);
+            if (px >= res || py >= res) continue;
 
-        // ---- primary ray (bvh_raycast.cpp:58-88)
-        const Vector3 horizontal = u * viewport;
-        const Vector3 vertical = vv * viewport;
-        const Vector3 lower_left = ray_start - horizontal / 2 - vertical / 2 + forward;
-        const float pu = ((float)px + 0.5f) / (float)res;
-        const float pv = ((float)py + 0.5f) / (float)res;
-        Vector3 ray_dir = lower_left + pu * horizontal + pv * vertical - ray_start;
-        ray_dir = ray_dir.normalize();
+            // ---- primary ray (bvh_raycast.cpp:58-88)
+            const Vector3 horizontal = u * viewport;
+            const Vector3 vertical = vv * viewport;
+            const Vector3 lower_left = ray_start - horizontal / 2 - vertical / 2 + forward;
+            const float pu = ((float)px + 0.5f) / (float)res;
+            const float pv = ((float)py + 0.5f) / (float)res;
+            Vector3 ray_dir = lower_left + pu * horizontal + pv * vertical - ray_start;
+            ray_dir = ray_dir.normalize();
 
-        const Diag3x3 inv_dir = Diag3x3::fromVec(ray_dir).inv();
-        float t_max = 10000.f;
-        int hit_inst = -1;
-        Vector3 hit_normal { 0, 0, 0 };
+            const RayHit first = traceWorld<false>(R, tlas, tlas_nodes, instances, ray_start, ray_dir, 0.f,
+                                                   10000.f, stack);
+            const bool hit = first.instance >= 0;
 
-        for (int k = 0; k < num_inst; k++) {
-            const RenderInstance &inst = staged[k];
-            AABB box { { inst.aabbMin[0], inst.aabbMin[1], inst.aabbMin[2] },
-                       { inst.aabbMax[0], inst.aabbMax[1], inst.aabbMax[2] } };
-            if (!box.rayIntersects(ray_start, inv_dir, 0.f, t_max)) continue;
-            const int first_tri = inst_tris[k];
-            if (first_tri == -2) continue;
-
-            // object-space ray; t is rescaled by |d'| while inside the mesh
-            const Quat q { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
-            const Diag3x3 inv_scale = Diag3x3 { inst.scale.x, inst.scale.y, inst.scale.z }.inv();
-            const Vector3 o { inst_origin[k][0], inst_origin[k][1], inst_origin[k][2] };
-            Vector3 d = inv_scale * q.inv().rotateVec(ray_dir);
-            const float t_scale = d.length();
-            float t_obj = t_max * t_scale;
-            d /= t_scale;
-            const Diag3x3 inv_d = Diag3x3::fromVec(d).inv();
-            const RayShear rs = rayShear(d, inv_d);
-
-            const MeshDesc &mesh = R.meshes[inst.objectID];
-            bool hit_here = false;
-            Vector3 n_obj { 0, 0, 0 };
-            if (first_tri >= 0) {
-                const float *tris = tri_arena + (size_t)first_tri * 9;
-                const bool flip = rs.kx != (rs.kz + 1) % 3;
-                switch (rs.kz * 2 + (flip ? 1 : 0)) {
-                case 0: stagedTriangles<0, false>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
-                case 1: stagedTriangles<0, true>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
-                case 2: stagedTriangles<1, false>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
-                case 3: stagedTriangles<1, true>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
-                case 4: stagedTriangles<2, false>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
-                default: stagedTriangles<2, true>(tris, mesh.numTriangles, rs.Sx, rs.Sy, rs.Sz, t_obj, hit_here, n_obj); break;
-                }
-            } else {
-                for (u32 tri = 0; tri < mesh.numTriangles; tri++) {
-                    const u32 *idx = R.indices + (size_t)(mesh.firstTriangle + tri) * 3;
-                    const Vector3 a { R.vertices[idx[0] * 3], R.vertices[idx[0] * 3 + 1], R.vertices[idx[0] * 3 + 2] };
-                    const Vector3 b { R.vertices[idx[1] * 3], R.vertices[idx[1] * 3 + 1], R.vertices[idx[1] * 3 + 2] };
-                    const Vector3 c { R.vertices[idx[2] * 3], R.vertices[idx[2] * 3 + 1], R.vertices[idx[2] * 3 + 2] };
-                    float t;
-                    Vector3 n;
-                    if (rayTriangle(a, b, c, rs, o, t_obj, &t, &n)) {
-                        t_obj = t;
-                        hit_here = true;
-                        n_obj = n;
-                    }
-                }
+            const size_t pix = (size_t)px + (size_t)py * res;
+            const size_t off = (size_t)view.outputRow * bytes_per_view + 4 * pix;
+            float *depth_out = (float *)((char *)out_tbl.columns[R.depthCol] + off);
+            *depth_out = hit ? first.t : 0.f;
+            if (R.hitIDs) {
+                i32 *ids = R.hitIDs + ((size_t)view.outputRow * res * res + pix) * 2;
+                ids[0] = hit ? first.instance : -1;
+                ids[1] = hit ? first.triangle : -1;
             }
-            t_max = t_obj / t_scale;
-            if (hit_here) {
-                hit_inst = k;
-                hit_normal = q.rotateVec(n_obj);
-            }
-        }
+            if (!R.rgbd) continue;
 
-        const size_t off = (size_t)view.outputRow * bytes_per_view + 4 * ((size_t)px + (size_t)py * res);
-        float *depth_out = (float *)((char *)out_tbl.columns[R.depthCol] + off);
-        *depth_out = hit_inst >= 0 ? t_max : 0.f;
-        if (R.rgbd) {
             unsigned char *rgb = (unsigned char *)out_tbl.columns[R.rgbCol] + off;
             Vector3 color { 0.f, 0.f, 0.f };
-            if (hit_inst >= 0) {
-                const u32 hex = staged[hit_inst].color;
-                const Vector3 base { ((hex >> 16) & 0xFF) / 255.0f, ((hex >> 8) & 0xFF) / 255.0f,
-                                     (hex & 0xFF) / 255.0f };
-                // no lights: max(0.2, 0) * colour, clamped (bvh_raycast.cpp:921-925)
-                color = fmaxf(0.2f, 0.f) * base;
+            if (hit) {
+                // colour of the hit (bvh_raycast.cpp:756-815, textures excepted)
+                const RenderInstance &inst = instances[first.instance];
+                const MeshBVH &mesh = R.meshes[inst.objectID];
+                i32 material_idx = inst.matID;
+                if (material_idx == -1) {
+                    material_idx = mesh.materialIDX != -1 ? mesh.materialIDX
+                                                          : mesh.leafMats[first.triangle].matIDX;
+                }
+                Vector3 base { 1.f, 1.f, 1.f };
+                if (inst.matID == -2) {
+                    base = hexToRgb(inst.color);
+                } else if (material_idx >= 0 && R.materials) {
+                    const RenderMaterial &m = R.materials[material_idx];
+                    base = Vector3 { m.color[0], m.color[1], m.color[2] };
+                }
+                const Quat iq { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
+                const Vector3 normal = iq.rotateVec(first.normalObj);
+
+                // lights (bvh_raycast.cpp:861-919)
+                const Vector3 hit_pos = ray_start + first.t * ray_dir;
+                float light_contrib = 0.f;
+                for (i32 li = 0; li < num_lights; li++) {
+                    const RenderLight &l = lights[li];
+                    const Vector3 ldir_in { l.direction.x, l.direction.y, l.direction.z };
+                    Vector3 light_dir = -ldir_in;
+                    if (!l.directional) {
+                        light_dir = (Vector3 { l.position.x, l.position.y, l.position.z } - hit_pos).normalize();
+                        if (l.cutoff != -1.f) {
+                            float dd = dot(-light_dir, ldir_in);
+                            dd /= (light_dir.length() * ldir_in.length());
+                            const float angle = acosf(dd);
+                            if (fabsf(angle) > fabsf(l.cutoff)) continue;
+                        }
+                    }
+                    if (l.castShadow) {
+                        if (dot(light_dir, normal) > 0.f) {
+                            // The reference starts the shadow ray AT the fp32 hit point with tMin 1e-6
+                            // (bvh_raycast.cpp:893-901): whether it re-hits its own triangle then
+                            // depends on which side of the surface the rounded point fell (measured
+                            // here: ~10 % of lit pixels flicker).  Deliberate deviation: the origin is
+                            // lifted 1 mm along the surface normal (which faces the light in this branch).
+                            const RayHit shadow = traceWorld<true>(R, tlas, tlas_nodes, instances,
+                                                                   hit_pos + 0.001f * normal, light_dir, 0.000001f,
+                                                                   10000.f, stack);
+                            if (shadow.instance < 0) {
+                                light_contrib += fminf(fmaxf(dot(normal, light_dir), 0.f), 1.f);
+                            }
+                        }
+                    } else {
+                        light_contrib += fminf(fmaxf(dot(normal, light_dir), 0.f), 1.f);
+                    }
+                }
+                color = fmaxf(0.2f, light_contrib) * base;
                 color.x = fminf(1.f, color.x);
                 color.y = fminf(1.f, color.y);
                 color.z = fminf(1.f, color.z);
@@ -522,20 +827,25 @@ renderRaycastKernel(EngineState *Sp)
             rgb[2] = (unsigned char)(color.z * 255);
             rgb[3] = 255;
         }
-        (void)hit_normal;
-        }   // tiles of the view
     }
 }
 
 // ---- host side --------------------------------------------------------------------------------
 
-struct HostMeshDesc {       // layout of mb2_render_config::mesh_bvhs entries
-    u32 firstTriangle;
-    u32 numTriangles;
-    float aabbMin[3];
-    float aabbMax[3];
+struct LightCarrierArchetype {
+    u32 archetype;
+    i32 carrierCol, posCol, dirCol, typeCol, shadowCol, cutoffCol, intensityCol, activeCol;
 };
-static_assert(sizeof(HostMeshDesc) == sizeof(MeshDesc), "mesh descriptor layout");
+
+static std::vector<LightCarrierArchetype> &lightCarriers(Executor *ex)
+{
+    static std::vector<std::pair<Executor *, std::vector<LightCarrierArchetype>>> all;
+    for (auto &e : all) {
+        if (e.first == ex) return e.second;
+    }
+    all.emplace_back(ex, std::vector<LightCarrierArchetype>());
+    return all.back().second;
+}
 
 bool renderHostCreate(Executor *ex, const mb2_render_config *rc, std::string *err)
 {
@@ -549,28 +859,23 @@ bool renderHostCreate(Executor *ex, const mb2_render_config *rc, std::string *er
     ex->allocations.push_back(rh->dRender);
     RenderState &R = rh->hRender;
     if (rc && rc->render_resolution > 0) {
+        if (!rc->geo_bvh_data.mesh_bvhs || rc->geo_bvh_data.num_bvhs == 0) {
+            *err = "CudaBatchRenderConfig::geoBVHData is empty (build it with mb2_build_mesh_bvhs / "
+                   "render::AssetProcessor::makeBVHData)";
+            return false;
+        }
         R.enabled = 1;
         R.resolution = rc->render_resolution;
         R.rgbd = rc->render_mode == 0 ? 1u : 0u;
         R.nearPlane = rc->near_plane;
         R.farPlane = rc->far_plane;
-        R.numMeshes = rc->num_mesh_bvhs;
-        R.numTriangles = rc->num_triangles;
-        auto upload = [&](const void *src, size_t bytes, const void **dst) {
-            void *p = nullptr;
-            if (bytes == 0) bytes = 16;
-            if (cudaMalloc(&p, bytes) != cudaSuccess) return false;
-            ex->allocations.push_back(p);
-            if (src) cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
-            *dst = p;
-            return true;
-        };
-        if (!upload(rc->mesh_bvhs, sizeof(MeshDesc) * rc->num_mesh_bvhs, (const void **)&R.meshes) ||
-            !upload(rc->vertices, sizeof(float) * 3 * rc->num_vertices, (const void **)&R.vertices) ||
-            !upload(rc->indices, sizeof(u32) * 3 * rc->num_triangles, (const void **)&R.indices)) {
-            *err = "render asset upload failed";
-            return false;
-        }
+        // device pointers, adopted as they are (the reference frees them in its
+        // destructor, cuda_exec.cpp:2449-2485; here their owner is whoever built them)
+        R.meshes = (const MeshBVH *)rc->geo_bvh_data.mesh_bvhs;
+        R.numMeshes = (u32)rc->geo_bvh_data.num_bvhs;
+        R.materials = (const RenderMaterial *)rc->material_data.materials;
+        const char *dbg = getenv("MADRONA_B200_RENDER_DEBUG");
+        R.debugHits = (dbg && *dbg && *dbg != '0') ? 1u : 0u;
     }
     cudaMemcpy(rh->dRender, &R, sizeof(RenderState), cudaMemcpyHostToDevice);
     ex->hState->render = rh->dRender;
@@ -612,6 +917,7 @@ bool renderHostAfterRegistry(Executor *ex, std::string *err)
             ra.cols[RCObjectID] = col(a, R.cidObjectID);
             ra.cols[RCRenderable] = col(a, R.cidRenderable);
             ra.colorCol = col(a, R.cidColorOverride);
+            ra.matCol = col(a, R.cidMaterialOverride);
         }
         if (col(a, R.cidRenderCamera) >= 0 && col(a, R.cidPosition) >= 0 && col(a, R.cidRotation) >= 0) {
             if (R.numViewArchetypes >= (u32)kMaxRenderArchetypes) {
@@ -627,8 +933,41 @@ bool renderHostAfterRegistry(Executor *ex, std::string *err)
     }
     R.rgbCol = col(R.outputArchetype, R.cidRGB);
     R.depthCol = col(R.outputArchetype, R.cidDepth);
-    R.maxInstancesPerWorld = kStagedInstances;
+    R.lightCol = col(R.lightArchetype, R.cidLightDesc);
+    {
+        const char *v = getenv("MADRONA_B200_MAX_INSTANCES_PER_WORLD");
+        int cap = (v && *v) ? atoi(v) : 128;
+        R.maxInstancesPerWorld = std::min(std::max(cap, 8), 512);
+    }
     R.maxViews = S.tables[R.outputArchetype].capacity;
+    rh->tlasSmem = tlasScratchBytes(R.maxInstancesPerWorld);
+    cudaFuncSetAttribute(renderBuildTLASKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rh->tlasSmem);
+
+    // light carriers: archetypes with LightCarrier + Position + every LightDesc* component
+    // (component ids are consecutive from registration: LightDesc, Direction, Type, Shadow,
+    // CutoffAngle, Intensity, Active, LightCarrier)
+    {
+        auto &carriers = lightCarriers(ex);
+        carriers.clear();
+        const u32 c0 = R.cidLightDesc;
+        for (u32 a = 0; a < S.numArchetypes; a++) {
+            if (!S.archetypes[a].registered) continue;
+            LightCarrierArchetype lc;
+            lc.archetype = a;
+            lc.carrierCol = col(a, c0 + 7);
+            lc.posCol = col(a, R.cidPosition);
+            lc.dirCol = col(a, c0 + 1);
+            lc.typeCol = col(a, c0 + 2);
+            lc.shadowCol = col(a, c0 + 3);
+            lc.cutoffCol = col(a, c0 + 4);
+            lc.intensityCol = col(a, c0 + 5);
+            lc.activeCol = col(a, c0 + 6);
+            if (lc.carrierCol >= 0 && lc.posCol >= 0 && lc.dirCol >= 0 && lc.typeCol >= 0 && lc.shadowCol >= 0 &&
+                    lc.cutoffCol >= 0 && lc.intensityCol >= 0 && lc.activeCol >= 0) {
+                carriers.push_back(lc);
+            }
+        }
+    }
 
     auto alloc = [&](void **p, size_t bytes) {
         if (cudaMalloc(p, bytes) != cudaSuccess) return false;
@@ -639,6 +978,12 @@ bool renderHostAfterRegistry(Executor *ex, std::string *err)
     const size_t W = S.numWorlds;
     if (!alloc((void **)&R.instances, sizeof(RenderInstance) * W * R.maxInstancesPerWorld) ||
         !alloc((void **)&R.instanceCounts, sizeof(i32) * W) ||
+        !alloc((void **)&R.tlasNodes, sizeof(QBVHNode) * W * R.maxInstancesPerWorld) ||
+        !alloc((void **)&R.tlasNodeCounts, sizeof(i32) * W) ||
+        !alloc((void **)&R.lights, sizeof(RenderLight) * W * kMaxLightsPerWorld) ||
+        !alloc((void **)&R.lightCounts, sizeof(i32) * W) ||
+        (R.debugHits && !alloc((void **)&R.hitIDs, sizeof(i32) * 2 * (size_t)R.maxViews * R.resolution *
+                                                       R.resolution)) ||
         !alloc((void **)&R.views, sizeof(RenderView) * (size_t)R.maxViews)) {
         *err = "render buffers allocation failed";
         return false;
@@ -653,21 +998,60 @@ void renderHostDestroy(Executor *ex)
     ex->render = nullptr;
 }
 
+__global__ void renderResetCountsKernel(EngineState *Sp)
+{
+    pdlSync();
+    Sp->render->totalNumInstances = 0;
+}
+
 bool renderEnqueuePrepare(Executor *ex, cudaStream_t s, std::string *err)
 {
     RenderHost *rh = ex->render;
     if (!rh || !rh->active) return true;   // rendering not configured: nothing to prepare
     (void)err;
+    const RenderState &R = rh->hRender;
     const unsigned W = ex->hState->numWorlds;
+    launchK(renderResetCountsKernel, dim3(1), dim3(1), 0, s, ex->dState);
     launchK(renderGatherInstancesKernel, dim3((W * 32 + 127) / 128), dim3(128), 0, s, ex->dState);
-    int max_cap = 256;
-    for (u32 i = 0; i < rh->hRender.numViewArchetypes; i++) {
-        max_cap = std::max(max_cap, ex->hState->tables[rh->hRender.viewers[i].archetype].capacity);
+    // lights: carriers refresh their light entities, the light table is brought into
+    // world order (no-op when clean), then listed per world
+    for (const LightCarrierArchetype &lc : lightCarriers(ex)) {
+        const int cap = ex->hState->tables[lc.archetype].capacity;
+        launchK(renderLightUpdateKernel, dim3((unsigned)std::max(1, std::min((cap + 255) / 256, ex->numSMs * 2))),
+                dim3(256), 0, s, ex->dState, lc.archetype, lc.carrierCol, lc.posCol, lc.dirCol, lc.typeCol,
+                lc.shadowCol, lc.cutoffCol, lc.intensityCol, lc.activeCol);
     }
-    dim3 grid((unsigned)std::min((max_cap + 255) / 256, ex->numSMs * 4),
-              std::max(rh->hRender.numViewArchetypes, 1u));
+    launchSortArchetype(ex, R.lightArchetype, 1, s);
+    launchK(renderGatherLightsKernel, dim3((W + 255) / 256), dim3(256), 0, s, ex->dState);
+    int max_cap = 256;
+    for (u32 i = 0; i < R.numViewArchetypes; i++) {
+        max_cap = std::max(max_cap, ex->hState->tables[R.viewers[i].archetype].capacity);
+    }
+    dim3 grid((unsigned)std::min((max_cap + 255) / 256, ex->numSMs * 4), std::max(R.numViewArchetypes, 1u));
     launchK(renderGatherViewsKernel, dim3(grid), dim3(256), 0, s, ex->dState);
+    launchK(renderBuildTLASKernel, dim3(W), dim3(32), rh->tlasSmem, s, ex->dState);
     return true;
+}
+
+void *renderDebugHitBuffer(Executor *ex)
+{
+    RenderHost *rh = ex->render;
+    return (rh && rh->active) ? (void *)rh->hRender.hitIDs : nullptr;
+}
+
+void *renderDebugBuffer(Executor *ex, int which, int64_t *stride_out)
+{
+    RenderHost *rh = ex->render;
+    if (!rh || !rh->active) return nullptr;
+    const RenderState &R = rh->hRender;
+    *stride_out = R.maxInstancesPerWorld;
+    switch (which) {
+    case 1: return R.tlasNodes;
+    case 2: return R.tlasNodeCounts;
+    case 3: return R.instances;
+    case 4: return R.instanceCounts;
+    default: return nullptr;
+    }
 }
 
 LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err)
@@ -702,11 +1086,13 @@ LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err)
     return g;
 }
 
-uint64_t renderBytesPerFrame(Executor *ex)
+// algorithmic bytes of one frame: res^2 x 4 B depth (+ 4 B RGBA8) per view
+uint64_t renderBytesPerFrame(Executor *ex, int64_t num_views)
 {
     RenderHost *rh = ex->render;
     if (!rh || !rh->active) return 0;
-    return 0;
+    const RenderState &R = rh->hRender;
+    return (uint64_t)num_views * R.resolution * R.resolution * (R.rgbd ? 8ull : 4ull);
 }
 
 }

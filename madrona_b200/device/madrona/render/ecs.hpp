@@ -24,6 +24,36 @@ struct Renderable {
     Entity renderEntity;      // none() => not drawn
 };
 
+struct LightCarrier {
+    Entity light;
+};
+
+// == include/madrona/render/ecs.hpp:65-115
+struct LightDesc {
+    enum Type : bool {
+        Directional = true,
+        Spotlight = false
+    };
+    Type type;
+    bool castShadow;
+    math::Vector3 position;
+    math::Vector3 direction;
+    float cutoff;
+    float intensity;
+    bool active;
+};
+
+struct LightDescDirection : math::Vector3 {
+    LightDescDirection(math::Vector3 v) : Vector3(v) {}
+};
+struct LightDescType { LightDesc::Type type; };
+struct LightDescShadow { bool castShadow; };
+struct LightDescCutoffAngle { float cutoff; };
+struct LightDescIntensity { float intensity; };
+struct LightDescActive { bool active; };
+
+struct LightArchetype : public Archetype<LightDesc> {};
+
 struct MaterialOverride {
     enum {
         UseDefaultMaterial = -1,
@@ -59,6 +89,14 @@ inline void registerTypes(ECSRegistry &registry, const RenderECSBridge *)
     registry.registerComponent<Renderable>();
     registry.registerComponent<MaterialOverride>();
     registry.registerComponent<ColorOverride>();
+    registry.registerComponent<LightDesc>();
+    registry.registerComponent<LightDescDirection>();
+    registry.registerComponent<LightDescType>();
+    registry.registerComponent<LightDescShadow>();
+    registry.registerComponent<LightDescCutoffAngle>();
+    registry.registerComponent<LightDescIntensity>();
+    registry.registerComponent<LightDescActive>();
+    registry.registerComponent<LightCarrier>();
 
     // one output row per view: res x res RGBA8 and res x res f32 depth
     // (src/render/ecs_system.cpp: registerComponent<...OutputBuffer>(bytes))
@@ -68,7 +106,11 @@ inline void registerTypes(ECSRegistry &registry, const RenderECSBridge *)
     registry.registerComponent<RGBOutputBuffer>(bytes);
     registry.registerComponent<DepthOutputBuffer>(bytes);
     registry.registerArchetype<RaycastOutputArchetype>();
+    registry.registerArchetype<LightArchetype>();
 
+    R.cidMaterialOverride = TypeTracker::typeID<MaterialOverride>();
+    R.lightArchetype = TypeTracker::typeID<LightArchetype>();
+    R.cidLightDesc = TypeTracker::typeID<LightDesc>();
     R.cidRenderable = TypeTracker::typeID<Renderable>();
     R.cidRenderCamera = TypeTracker::typeID<RenderCamera>();
     R.cidColorOverride = TypeTracker::typeID<ColorOverride>();
@@ -111,6 +153,24 @@ inline void cleanupViewingEntity(Context &ctx, Entity e)
 inline void cleanupRenderableEntity(Context &ctx, Entity e)
 {
     ctx.get<Renderable>(e).renderEntity = Entity::none();
+}
+
+// src/render/ecs_system.cpp:713-727: the light entity takes its description from
+// the carrier's LightDesc* components; the prepare node refreshes position /
+// direction / state from the carrier every step (lightUpdate, :183-209)
+inline void makeEntityLightCarrier(Context &ctx, Entity e)
+{
+    Entity light_e = ctx.makeEntity<LightArchetype>();
+    ctx.get<LightCarrier>(e).light = light_e;
+    LightDesc desc;
+    desc.type = ctx.get<LightDescType>(e).type;
+    desc.castShadow = ctx.get<LightDescShadow>(e).castShadow;
+    desc.position = ctx.get<base::Position>(e);
+    desc.direction = ctx.get<LightDescDirection>(e);
+    desc.cutoff = ctx.get<LightDescCutoffAngle>(e).cutoff;
+    desc.intensity = ctx.get<LightDescIntensity>(e).intensity;
+    desc.active = ctx.get<LightDescActive>(e).active;
+    ctx.get<LightDesc>(light_e) = desc;
 }
 
 // Per step: gather instance transforms / world boxes and camera data for the

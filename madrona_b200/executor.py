@@ -36,6 +36,14 @@ EXPORTED_SYMBOLS = [
     "mb2_jit_precompile",
     "mb2_profile_nodes",
     "mb2_version",
+    "mb2_init_cuda_ctx",
+    "mb2_device_of_context",
+    "mb2_build_mesh_bvhs",
+    "mb2_mesh_bvh_data_view",
+    "mb2_mesh_bvh_triangle_sources",
+    "mb2_mesh_bvh_data_destroy",
+    "mb2_render_debug_hits",
+    "mb2_render_debug_buffer",
     "mb2_peer_gather_create",
     "mb2_peer_gather_local_handle",
     "mb2_peer_gather_connect",
@@ -75,18 +83,37 @@ class _CompileConfigC(ctypes.Structure):
     ]
 
 
-class _RenderConfigC(ctypes.Structure):
+class _MeshBVHViewC(ctypes.Structure):       # == render::MeshBVHData
+    _fields_ = [
+        ("nodes", ctypes.c_void_p), ("num_nodes", ctypes.c_uint64),
+        ("leaf_material", ctypes.c_void_p), ("num_leaves", ctypes.c_uint64),
+        ("vertices", ctypes.c_void_p), ("num_verts", ctypes.c_uint64),
+        ("mesh_bvhs", ctypes.c_void_p), ("num_bvhs", ctypes.c_uint64),
+    ]
+
+
+class _MaterialViewC(ctypes.Structure):      # == render::MaterialData
+    _fields_ = [
+        ("textures", ctypes.c_void_p), ("num_texture_buffers", ctypes.c_uint32),
+        ("texture_buffers", ctypes.c_void_p), ("materials", ctypes.c_void_p),
+    ]
+
+
+class _RenderConfigC(ctypes.Structure):      # == madrona::CudaBatchRenderConfig
     _fields_ = [
         ("render_mode", ctypes.c_uint32),
+        ("geo_bvh_data", _MeshBVHViewC),
+        ("material_data", _MaterialViewC),
         ("render_resolution", ctypes.c_uint32),
         ("near_plane", ctypes.c_float),
         ("far_plane", ctypes.c_float),
-        ("mesh_bvhs", ctypes.c_void_p),
-        ("num_mesh_bvhs", ctypes.c_uint32),
-        ("vertices", ctypes.c_void_p),
-        ("num_vertices", ctypes.c_uint32),
-        ("indices", ctypes.c_void_p),
-        ("num_triangles", ctypes.c_uint32),
+    ]
+
+
+class _MeshSourceC(ctypes.Structure):
+    _fields_ = [
+        ("positions", ctypes.c_void_p), ("uvs", ctypes.c_void_p), ("num_vertices", ctypes.c_uint32),
+        ("indices", ctypes.c_void_p), ("num_triangles", ctypes.c_uint32), ("material_idx", ctypes.c_int32),
     ]
 
 
@@ -149,6 +176,18 @@ def load_library() -> ctypes.CDLL:
     lib.mb2_profile_nodes.restype = ctypes.c_int64
     lib.mb2_version.argtypes = []
     lib.mb2_version.restype = ctypes.c_char_p
+    lib.mb2_build_mesh_bvhs.argtypes = [ctypes.POINTER(_MeshSourceC), ctypes.c_uint32, ctypes.c_int]
+    lib.mb2_build_mesh_bvhs.restype = vp
+    lib.mb2_mesh_bvh_data_view.argtypes = [vp, ctypes.c_int]
+    lib.mb2_mesh_bvh_data_view.restype = ctypes.POINTER(_MeshBVHViewC)
+    lib.mb2_mesh_bvh_triangle_sources.argtypes = [vp]
+    lib.mb2_mesh_bvh_triangle_sources.restype = ctypes.POINTER(ctypes.c_uint32)
+    lib.mb2_mesh_bvh_data_destroy.argtypes = [vp]
+    lib.mb2_mesh_bvh_data_destroy.restype = None
+    lib.mb2_render_debug_hits.argtypes = [vp]
+    lib.mb2_render_debug_hits.restype = vp
+    lib.mb2_render_debug_buffer.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+    lib.mb2_render_debug_buffer.restype = vp
     lib.mb2_peer_gather_create.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_uint32,
                                            ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint32, ctypes.c_uint32]
     lib.mb2_peer_gather_create.restype = vp
@@ -364,6 +403,32 @@ class MWCudaExecutor:
         from .tensor import Tensor
         return Tensor(self.getExported(slot), type, dimensions, gpu_id=self.gpu_id)
 
+    def renderDebugHits(self, num_views: int, resolution: int):
+        """int32 [views, res, res, 2] (instance, triangle) per pixel; needs MADRONA_B200_RENDER_DEBUG=1."""
+        import torch
+        p = self._lib.mb2_render_debug_hits(self._h)
+        if not p:
+            raise MadronaB200Error("no debug hit buffer (set MADRONA_B200_RENDER_DEBUG=1 before creating the executor)")
+        view = _CudaView(p, (num_views, resolution, resolution, 2), "<i4")
+        return torch.as_tensor(view, device=f"cuda:{self.gpu_id}")
+
+    def renderDebugStructures(self):
+        """(tlas_nodes u8 [W, cap, 60], tlas_counts [W], instances u8 [W, cap, 76], instance_counts [W])
+        of the last render-prepare (test hook)."""
+        import torch
+        cap = ctypes.c_int64(0)
+        out = []
+        for which, (bytes_per, counts) in ((1, (60, False)), (2, (4, True)), (3, (76, False)), (4, (4, True))):
+            p = self._lib.mb2_render_debug_buffer(self._h, which, ctypes.byref(cap))
+            if not p:
+                raise MadronaB200Error("no renderer")
+            if counts:
+                view = _CudaView(p, (self.num_worlds,), "<i4")
+            else:
+                view = _CudaView(p, (self.num_worlds, cap.value, bytes_per), "|u1")
+            out.append(torch.as_tensor(view, device=f"cuda:{self.gpu_id}").cpu().numpy())
+        return out
+
     def peerGather(self, slots, shapes, dtypes, world_size: int, rank: int):
         """NVLink peer-store gather of fixed-size exported columns across the ranks of a
         node (include/madrona_b200.h, peer_gather.cu).  slots / shapes / dtypes describe
@@ -373,6 +438,59 @@ class MWCudaExecutor:
     def close(self) -> None:
         if self._h:
             self._lib.mb2_executor_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MeshBVHData:
+    """BLAS of a set of triangle meshes in the reference's MeshBVHData format (role of
+    render::AssetProcessor::makeBVHData): `view(device=True)` is what goes into
+    CudaBatchRenderConfig.geoBVHData.  meshes: list of (positions [nv,3] f32, indices
+    [nt,3] u32, material_idx)."""
+
+    def __init__(self, meshes, gpu_id: int = -1):
+        import numpy as np
+        self._lib = load_library()
+        self._keep = []
+        srcs = (_MeshSourceC * len(meshes))()
+        for i, (pos, idx, mat) in enumerate(meshes):
+            pos = np.ascontiguousarray(pos, dtype=np.float32)
+            idx = np.ascontiguousarray(idx, dtype=np.uint32)
+            self._keep += [pos, idx]
+            srcs[i] = _MeshSourceC(pos.ctypes.data, None, len(pos), idx.ctypes.data, len(idx), int(mat))
+        self.num_triangles = [len(m[1]) for m in meshes]
+        self._h = self._lib.mb2_build_mesh_bvhs(srcs, len(meshes), gpu_id)
+        if not self._h:
+            raise MadronaB200Error(_last_error(self._lib))
+
+    def view(self, device: bool = True) -> _MeshBVHViewC:
+        return self._lib.mb2_mesh_bvh_data_view(self._h, 1 if device else 0).contents
+
+    def triangle_sources(self):
+        """For every triangle of the concatenated BLAS order: its index in its source mesh."""
+        import numpy as np
+        n = sum(self.num_triangles)
+        ptr = self._lib.mb2_mesh_bvh_triangle_sources(self._h)
+        return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+    def host_arrays(self):
+        """(nodes bytes [n,60], vertices f32 [nv,5], per-mesh (first_node, num_nodes, first_tri, num_tris, root box))."""
+        import numpy as np
+        v = self.view(device=False)
+        nodes = np.ctypeslib.as_array(ctypes.cast(v.nodes, ctypes.POINTER(ctypes.c_uint8)),
+                                      shape=(v.num_nodes, 60)).copy()
+        verts = np.ctypeslib.as_array(ctypes.cast(v.vertices, ctypes.POINTER(ctypes.c_float)),
+                                      shape=(v.num_verts, 5)).copy()
+        return nodes, verts
+
+    def close(self):
+        if self._h:
+            self._lib.mb2_mesh_bvh_data_destroy(self._h)
             self._h = None
 
     def __del__(self):

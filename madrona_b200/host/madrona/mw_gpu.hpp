@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <type_traits>
 #include <utility>
@@ -21,8 +22,24 @@
 typedef struct CUctx_st *CUcontext;
 typedef struct CUstream_st *cudaStream_t;
 
+// A Manager usually includes other reference headers too (utils, span, optional,
+// importer, render assets).  When the reference's include directory is on the
+// include path (after this one), its own definitions are used; only what is
+// missing is declared here, with the reference's names and layouts.
+#if __has_include(<madrona/span.hpp>)
+#include <madrona/types.hpp>
+#include <madrona/span.hpp>
+#include <madrona/optional.hpp>
+#define MB2_FACADE_HAS_REFERENCE_CORE 1
+#endif
+#if __has_include(<madrona/render/cuda_batch_render_assets.hpp>) && __has_include(<cuda_runtime.h>)
+#include <madrona/render/cuda_batch_render_assets.hpp>
+#define MB2_FACADE_HAS_REFERENCE_RENDER 1
+#endif
+
 namespace madrona {
 
+#ifndef MB2_FACADE_HAS_REFERENCE_CORE
 using CountT = int64_t;
 
 template <typename T>
@@ -57,6 +74,30 @@ private:
     T v_ {};
     bool has_;
 };
+#endif
+
+#ifndef MB2_FACADE_HAS_REFERENCE_RENDER
+// == include/madrona/render/cuda_batch_render_assets.hpp (pointers are device
+// pointers to reference-format arrays, see madrona_b200/csrc/render_bvh.h)
+namespace render {
+struct MeshBVHData {
+    void *nodes;
+    uint64_t numNodes;
+    void *leafMaterial;
+    uint64_t numLeaves;
+    void *vertices;
+    uint64_t numVerts;
+    void *meshBVHs;
+    uint64_t numBVHs;
+};
+struct MaterialData {
+    void *textures;
+    uint32_t numTextureBuffers;
+    void *textureBuffers;
+    void *materials;
+};
+}
+#endif
 
 // == include/madrona/mw_gpu.hpp:25-51
 struct StateConfig {
@@ -83,14 +124,15 @@ struct CompileConfig {
     OptMode optMode = OptMode::LTO;
 };
 
-// == include/madrona/mw_gpu.hpp:75-96 (mesh data flattened, see madrona_b200.h)
+// == include/madrona/mw_gpu.hpp:75-96
 struct CudaBatchRenderConfig {
     enum class RenderMode : uint32_t {
         RGBD,
         Depth,
     };
     RenderMode renderMode;
-    mb2_render_config data {};
+    render::MeshBVHData geoBVHData;
+    render::MaterialData materialData;
     uint32_t renderResolution = 0;
     float nearPlane = 0.f;
     float farPlane = 0.f;
@@ -129,12 +171,14 @@ friend class MWCudaExecutor;
 
 class MWCudaExecutor {
 public:
-    // Initializes CUDA, sets the current device.  The returned handle only
-    // carries the GPU index (this engine uses the runtime's primary context).
+    // Initializes CUDA, sets the current device and returns the device's primary
+    // context (the reference creates its own context, cuda_exec.cpp:2315-2331;
+    // this engine runs on the runtime's primary context so torch can share it).
     static CUcontext initCUDA(int gpu_id)
     {
-        if (mb2_init_cuda(gpu_id) != 0) detail::fatal("initCUDA");
-        return (CUcontext)(uintptr_t)(gpu_id + 1);
+        void *ctx = nullptr;
+        if (mb2_init_cuda_ctx(gpu_id, &ctx) != 0) detail::fatal("initCUDA");
+        return (CUcontext)ctx;
     }
 
     MWCudaExecutor() : h_(nullptr) {}
@@ -157,13 +201,18 @@ public:
         };
         mb2_render_config rc {};
         if (render_cfg.has_value()) {
-            rc = render_cfg->data;
+            static_assert(sizeof(render::MeshBVHData) == sizeof(mb2_mesh_bvh_view), "MeshBVHData layout");
             rc.render_mode = (uint32_t)render_cfg->renderMode;
+            memcpy(&rc.geo_bvh_data, &render_cfg->geoBVHData, sizeof(rc.geo_bvh_data));
+            rc.material_data.textures = (void *)render_cfg->materialData.textures;
+            rc.material_data.num_texture_buffers = render_cfg->materialData.numTextureBuffers;
+            rc.material_data.texture_buffers = (void *)render_cfg->materialData.textureBuffers;
+            rc.material_data.materials = (void *)render_cfg->materialData.materials;
             rc.render_resolution = render_cfg->renderResolution;
             rc.near_plane = render_cfg->nearPlane;
             rc.far_plane = render_cfg->farPlane;
         }
-        int gpu_id = cu_ctx ? (int)(uintptr_t)cu_ctx - 1 : 0;
+        int gpu_id = mb2_device_of_context((void *)cu_ctx);
         h_ = mb2_executor_create(&sc, &cc, gpu_id, render_cfg.has_value() ? &rc : nullptr);
         if (!h_) detail::fatal("MWCudaExecutor");
     }

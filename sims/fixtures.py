@@ -84,7 +84,8 @@ def _arena_objects():
 
 def _room_render_cfg(cfg):
     from .render_assets import make_render_config
-    return make_render_config(int(cfg.get("resolution", 64)), bool(cfg.get("rgbd", False)))
+    return make_render_config(int(cfg.get("resolution", 64)), bool(cfg.get("rgbd", False)),
+                              gpu_id=int(cfg.get("_gpu_id", 0)))
 
 
 SIMS: Dict[str, SimDesc] = {
@@ -200,6 +201,21 @@ SIMS: Dict[str, SimDesc] = {
         objects=_balls_objects,
         compile_flags=["-DBALLS_MANY=1"],
     ),
+    # GPU only: batch ray caster with a real TLAS / BLAS, materials, lights (tests/test_render_bvh.py)
+    "gallery": SimDesc(
+        name="gallery",
+        sources=[os.path.join(_ROOT, "gallery", "sim.cpp")],
+        num_exports=10,
+        num_taskgraphs=1,
+        inputs=[],
+        outputs=[],
+        pack_config=lambda cfg: struct.pack("<II", int(cfg["num_props"]), 5),
+        pack_init=lambda w, cfg: struct.pack("<I", int(cfg.get("seed", 0)) + w),
+        oracle_extra=lambda cfg: [],
+        defaults={"num_props": 100, "seed": 0, "resolution": 40, "rgbd": True},
+        render=lambda cfg: __import__("sims.render_assets", fromlist=["x"]).make_gallery_render_config(
+            int(cfg.get("resolution", 40)), bool(cfg.get("rgbd", True)), gpu_id=int(cfg.get("_gpu_id", 0))),
+    ),
     # GPU only: 145 bodies per world, past the per-world body cap (tests/test_cliffs.py)
     "balls_cliff": SimDesc(
         name="balls_cliff",
@@ -290,6 +306,7 @@ def make_executor(name: str, num_worlds: int, gpu_id: int = 0, objects_fn=None, 
     compile_cfg = mb.CompileConfig(userSources=desc.sources,
                                    userCompileFlags=["-I" + os.path.dirname(desc.sources[0])] +
                                    list(desc.compile_flags))
+    full["_gpu_id"] = gpu_id
     render_cfg, render_keep = (desc.render(full) if desc.render is not None else (None, None))
     ex = mb.MWCudaExecutor(state, compile_cfg, gpu_id=gpu_id, render_cfg=render_cfg)
     ex._keep_alive = (keep_alive, render_keep)

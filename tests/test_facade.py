@@ -43,3 +43,26 @@ def test_facade_runs_cartpole(tmp_path):
     ins = {"reset": np.zeros((10, 64, 1), np.int32), "action": np.zeros((10, 64, 1), np.int32)}
     ref, _ = rollout_gpu("cartpole", 64, 10, ins, {"max_steps": 200, "seed": 0})
     assert np.allclose(got, ref["state"][10, 0], rtol=0, atol=0)
+
+
+REF_INCLUDE = "/root/reference/include"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INCLUDE), reason="reference headers not on this box")
+def test_reference_style_manager_compiles_against_reference_headers_plus_facade(tmp_path):
+    # A Manager that includes the reference's <madrona/utils.hpp>, <madrona/span.hpp>,
+    # <madrona/optional.hpp>, <madrona/heap_array.hpp> AND <madrona/mw_gpu.hpp> (the facade:
+    # madrona_b200/host comes first on the include path), with CudaBatchRenderConfig filled the
+    # reference way (render::MeshBVHData / render::MaterialData from the reference's
+    # cuda_batch_render_assets.hpp): no redefinitions, links against libmadrona_b200.so.
+    exe = str(tmp_path / "facade_reference_mgr")
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-D_LIBCPP_VERSION=190000",
+           "-include", os.path.join(ROOT, "tests", "cpp", "ref_shim.h"),
+           "-I" + os.path.join(ROOT, "madrona_b200", "host"), "-I" + REF_INCLUDE, "-I/usr/local/cuda/include",
+           os.path.join(ROOT, "tests", "cpp", "facade_reference_mgr.cpp"), "-o", exe,
+           "-L" + os.path.join(ROOT, "madrona_b200"), "-lmadrona_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "madrona_b200"), "-L/usr/local/cuda/lib64", "-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    # built only: without arguments the program returns before touching CUDA
+    assert subprocess.run([exe]).returncode == 0
