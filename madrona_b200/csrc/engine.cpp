@@ -130,6 +130,11 @@ static bool allocateTables(Executor *ex)
         t.isSingleton = info.isSingleton;
         t.numRows = info.isSingleton ? (int32_t)W : 0;
 
+        // dynamic archetypes live in growable address ranges (up to 64x the initial
+        // capacity, the row index stays a positive int32); fixed ones are W x max rows for good
+        const bool growable = ex->tableGrowth && !info.isSingleton && info.maxPerWorld == 0;
+        const uint64_t reserve_rows = std::min<uint64_t>(cap * 64, 0x7fffff00ull);
+        if (growable) ex->columnRanges[a].resize(t.numColumns);
         for (int32_t c = 0; c < t.numColumns; c++) {
             uint32_t cid = c == 0 ? 0u : (c == 1 ? 1u : info.componentIDs[c - 2]);
             if (cid >= S.numComponents) {
@@ -138,7 +143,17 @@ static bool allocateTables(Executor *ex)
             }
             uint32_t bytes = S.components[cid].numBytes;
             t.columnBytes[c] = bytes;
-            if (!devAlloc(ex, &t.columns[c], (size_t)bytes * cap + 256)) return false;
+            if (growable) {
+                std::string verr;
+                if (!vmReserve(ex->gpu, &ex->columnRanges[a][c], (size_t)bytes * reserve_rows + 256,
+                               (size_t)bytes * cap + 256, &verr)) {
+                    setError(verr);
+                    return false;
+                }
+                t.columns[c] = ex->columnRanges[a][c].base;
+            } else if (!devAlloc(ex, &t.columns[c], (size_t)bytes * cap + 256)) {
+                return false;
+            }
             S.columnLookup[a][cid] = (i16)c;
         }
         if (!devAlloc(ex, (void **)&t.worldOffsets, sizeof(int32_t) * W)) return false;
@@ -178,7 +193,17 @@ static bool allocateTables(Executor *ex)
     S.initExpandBlocks = (int32_t)init_blocks;
     S.numEntitySlots = (int32_t)(init_blocks * kIDsPerCache);
     S.freeHead = ((u64)0 << 32) | (u32)kIDSentinel;
-    if (!devAlloc(ex, (void **)&S.entitySlots, sizeof(EntitySlot) * ent_cap)) return false;
+    if (ex->tableGrowth) {
+        std::string verr;
+        if (!vmReserve(ex->gpu, &ex->entityRange, sizeof(EntitySlot) * 0x7fffff00ull, sizeof(EntitySlot) * ent_cap,
+                       &verr)) {
+            setError(verr);
+            return false;
+        }
+        S.entitySlots = (EntitySlot *)ex->entityRange.base;
+    } else if (!devAlloc(ex, (void **)&S.entitySlots, sizeof(EntitySlot) * ent_cap)) {
+        return false;
+    }
     if (!devAlloc(ex, (void **)&S.idCaches, sizeof(IDCache) * W)) return false;
 
     S.tmpCapacity = envU64("MADRONA_B200_TMP_BYTES", 256ull << 20);
@@ -187,6 +212,67 @@ static bool allocateTables(Executor *ex)
     if (!devAlloc(ex, (void **)&S.persistArena, S.persistCapacity)) return false;
     S.tmpOffset = 0;
     S.persistOffset = 0;
+    return true;
+}
+
+}   // namespace mb2 (reopened below)
+
+namespace mb2 {
+
+bool growTable(Executor *ex, uint32_t a, int64_t new_cap, std::string *err)
+{
+    EngineState &S = *ex->hState;
+    TableDesc &t = S.tables[a];
+    if (ex->columnRanges[a].empty()) {
+        *err = "archetype " + std::to_string(a) + " has a fixed size";
+        return false;
+    }
+    new_cap = (new_cap + 255) & ~255ll;
+    if (new_cap <= t.capacity) return true;
+    if (new_cap > 0x7fffff00ll) {
+        *err = "table too large";
+        return false;
+    }
+    const int64_t added = new_cap - t.capacity;
+    for (int32_t c = 0; c < t.numColumns; c++) {
+        const size_t bytes = (size_t)t.columnBytes[c] * (size_t)new_cap + 256;
+        if (!vmGrow(ex->gpu, &ex->columnRanges[a][c], bytes, err)) return false;
+        if (!ex->twinRanges[a].empty() && !vmGrow(ex->gpu, &ex->twinRanges[a][c], bytes, err)) return false;
+    }
+    if (ex->sortScratch && !sortScratchEnsure(ex, (int32_t)new_cap, err)) return false;
+    // one entity slot per possible row
+    const int64_t new_ent = std::min<int64_t>((int64_t)S.entityCapacity + added, 0x7fffff00ll);
+    if (!vmGrow(ex->gpu, &ex->entityRange, sizeof(EntitySlot) * (size_t)new_ent, err)) return false;
+    S.entityCapacity = (int32_t)new_ent;
+    t.capacity = (int32_t)new_cap;
+    cudaMemcpy(&ex->dState->tables[a].capacity, &t.capacity, sizeof(int32_t), cudaMemcpyHostToDevice);
+    cudaMemcpy(&ex->dState->entityCapacity, &S.entityCapacity, sizeof(int32_t), cudaMemcpyHostToDevice);
+    ex->growthEvents++;
+    if (getenv("MADRONA_B200_VERBOSE")) {
+        fprintf(stderr, "[madrona_b200] archetype %u grown to %ld rows\n", a, (long)new_cap);
+    }
+    return true;
+}
+
+// Between steps: a dynamic table whose row count peaked above half its capacity during
+// the last graph gets twice the room (so that one step can at most double a table
+// without overflowing -- the worst case of a full reset before compaction).
+static bool growTablesFromStatus(Executor *ex)
+{
+    if (!ex->tableGrowth) return true;
+    EngineState &S = *ex->hState;
+    for (uint32_t a = 0; a < S.numArchetypes && a < (uint32_t)kMaxArchetypes; a++) {
+        if (ex->columnRanges[a].empty()) continue;
+        const int64_t peak = ex->hStatus[2 + a];
+        int64_t cap = S.tables[a].capacity;
+        if (peak * 2 <= cap) continue;
+        while (cap < peak * 2) cap *= 2;
+        std::string err;
+        if (!growTable(ex, a, cap, &err)) {
+            setError("table growth: " + err);
+            return false;
+        }
+    }
     return true;
 }
 
@@ -265,6 +351,7 @@ static bool createExecutor(Executor *ex, const mb2_state_config *sc,
     MB2_CUDA(cudaStreamCreate(&ex->stream));
     ex->rowsPerWorldHint = envU64("MADRONA_B200_ROWS_PER_WORLD", 128);
     g_pdl = envU64("MADRONA_B200_PDL", 0) != 0;
+    ex->tableGrowth = envU64("MADRONA_B200_TABLE_GROWTH", 1) != 0;
 
     // ---- JIT the simulator
     std::vector<std::string> sources, flags;
@@ -299,8 +386,8 @@ static bool createExecutor(Executor *ex, const mb2_state_config *sc,
     MB2_CUDA(cudaMalloc((void **)&ex->dState, sizeof(EngineState)));
     ex->allocations.push_back(ex->dState);
     MB2_CUDA(cudaMemset(ex->dState, 0, sizeof(EngineState)));
-    MB2_CUDA(cudaMallocHost((void **)&ex->hStatus, 64));
-    memset(ex->hStatus, 0, 64);
+    MB2_CUDA(cudaMallocHost((void **)&ex->hStatus, sizeof(uint32_t) * kStatusWords));
+    memset(ex->hStatus, 0, sizeof(uint32_t) * kStatusWords);
 
     EngineState &S = *ex->hState;
     S.numWorlds = sc->num_worlds;
@@ -361,9 +448,25 @@ static bool createExecutor(Executor *ex, const mb2_state_config *sc,
 
     // ---- phase 3: world constructors, two passes (see mb2_state.h IDCache)
     const unsigned wblocks = (S.numWorlds + 127) / 128;
-    if (!resetForInitPass(ex, 0, {}, persist_mark)) return false;
-    if (!launch1(ex, ex->initWorlds, wblocks, 128)) return false;
-    if (!checkDeviceErrors(ex, "world construction (dry run)")) return false;
+    for (int attempt = 0;; attempt++) {
+        if (!resetForInitPass(ex, 0, {}, persist_mark)) return false;
+        if (!launch1(ex, ex->initWorlds, wblocks, 128)) return false;
+        // a dynamic table too small for the worlds' initial population: double it and
+        // construct again (the dry run exists to be repeated)
+        uint32_t st[2] = { 0, 0 };
+        MB2_CUDA(cudaMemcpy(st, &ex->dState->errorFlags, sizeof(st), cudaMemcpyDeviceToHost));
+        if (st[0] == (uint32_t)ErrTableOverflow && ex->tableGrowth && attempt < 12 &&
+                st[1] < S.numArchetypes && !ex->columnRanges[st[1]].empty()) {
+            std::string gerr;
+            if (!growTable(ex, st[1], (int64_t)S.tables[st[1]].capacity * 2, &gerr)) {
+                setError("world construction: " + gerr);
+                return false;
+            }
+            continue;
+        }
+        if (!checkDeviceErrors(ex, "world construction (dry run)")) return false;
+        break;
+    }
 
     std::vector<IDCache> caches(S.numWorlds);
     MB2_CUDA(cudaMemcpy(caches.data(), S.idCaches, sizeof(IDCache) * S.numWorlds,
@@ -429,6 +532,11 @@ static void destroyExecutor(Executor *ex)
     physicsHostDestroy(ex);
     renderHostDestroy(ex);
     sortScratchDestroy(ex);
+    for (int a = 0; a < kMaxArchetypes; a++) {
+        for (VMRange &r : ex->columnRanges[a]) vmRelease(&r);
+        for (VMRange &r : ex->twinRanges[a]) vmRelease(&r);
+    }
+    vmRelease(&ex->entityRange);
     for (void *p : ex->allocations) cudaFree(p);
     if (ex->hStatus) cudaFreeHost(ex->hStatus);
     if (ex->lib) cudaLibraryUnload(ex->lib);
@@ -960,6 +1068,11 @@ int mb2_run_async(mb2_executor *exec, mb2_launch_graph *graph, void *cuda_stream
         setError("null executor or launch graph");
         return 1;
     }
+    // an idle executor can act on the status its last graph published (table growth)
+    if ((cudaStream_t)cuda_stream != ex->stream && ex->tableGrowth &&
+            cudaStreamQuery((cudaStream_t)cuda_stream) == cudaSuccess && cudaStreamQuery(ex->stream) == cudaSuccess) {
+        if (ex->hStatus[0] == 0 && !growTablesFromStatus(ex)) return 1;
+    }
     cudaError_t e = cudaGraphLaunch(g->exec, (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) {
         setError(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
@@ -981,6 +1094,7 @@ int mb2_run(mb2_executor *exec, mb2_launch_graph *graph)
         setError("step failed: " + describeErrors(ex->hStatus[0], ex->hStatus[1]));
         return 2;
     }
+    if (!growTablesFromStatus(ex)) return 1;
     return 0;
 }
 

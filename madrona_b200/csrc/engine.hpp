@@ -8,6 +8,7 @@
 
 #include "mb2_state.h"
 #include "jit.hpp"
+#include "vm_alloc.hpp"
 
 namespace mb2 {
 
@@ -40,7 +41,19 @@ struct Executor {
     RenderHost *render = nullptr;
 
     uint64_t rowsPerWorldHint = 64;
+
+    // ---- growable storage (vm_alloc.hpp): dynamic archetypes' columns and their sort
+    // twins, the sort's key / index / look-back scratch and the entity store keep their
+    // base address and get more physical memory between steps
+    bool tableGrowth = true;                                   // MADRONA_B200_TABLE_GROWTH
+    std::vector<VMRange> columnRanges[kMaxArchetypes];         // [archetype][column]; empty: fixed table
+    std::vector<VMRange> twinRanges[kMaxArchetypes];
+    VMRange entityRange;
+    int64_t growthEvents = 0;
 };
+
+// status block published by the last kernel of every launch graph (pinned host memory)
+constexpr int kStatusWords = 2 + kMaxArchetypes;   // errorFlags, errorArchetype, peak rows per table
 
 struct LaunchGraph {
     Executor *owner = nullptr;
@@ -95,5 +108,9 @@ void sortScratchDestroy(Executor *ex);
 // additionally drops rows with key -1 and rebuilds worldOffsets/worldCounts.
 void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStream_t s);
 int sortNumPasses(Executor *ex, int32_t col);
+// the sort's key / index / look-back scratch must cover the largest table
+bool sortScratchEnsure(Executor *ex, int32_t max_rows, std::string *err);
+// grow a dynamic table to new_capacity rows (columns, twins, entity store, sort scratch)
+bool growTable(Executor *ex, uint32_t archetype, int64_t new_capacity, std::string *err);
 
 }

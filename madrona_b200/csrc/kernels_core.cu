@@ -37,6 +37,13 @@ __global__ void statusCopyKernel(EngineState *S, uint32_t *host_status)
     pdlSync();
     host_status[0] = S->errorFlags;
     host_status[1] = S->errorArchetype;
+    // peak row count of every table during this graph (the host grows tables between steps)
+    for (uint32_t a = threadIdx.x; a < S->numArchetypes; a += blockDim.x) {
+        TableDesc &t = S->tables[a];
+        const uint32_t rows = (uint32_t)max(t.numRows, 0);
+        host_status[2 + a] = rows > t.highWater ? rows : t.highWater;
+        t.highWater = rows;
+    }
 }
 
 // Singleton archetypes: one row per world, row == world, created at
@@ -77,7 +84,7 @@ void launchResetTmpAlloc(Executor *ex, cudaStream_t s)
 
 void launchStatusCopy(Executor *ex, cudaStream_t s)
 {
-    launchK(statusCopyKernel, dim3(1), dim3(1), 0, s, ex->dState, ex->hStatus);
+    launchK(statusCopyKernel, dim3(1), dim3(32), 0, s, ex->dState, ex->hStatus);
 }
 
 void launchFillSingletons(Executor *ex, cudaStream_t s)

@@ -44,7 +44,8 @@ struct SortScratch {
     uint32_t *keys[2] = {};
     int32_t *idx[2] = {};
     int32_t *bins = nullptr;        // [kMaxPasses][256]
-    uint32_t *lookback = nullptr;   // [kMaxPasses][maxTiles][256]
+    uint32_t *lookback = nullptr;   // [tile][kMaxPasses][256] (layout independent of the table size)
+    VMRange keyRanges[2], idxRanges[2], lookbackRange;
     SortCtrl *ctrl = nullptr;
     void **altColumns = nullptr;    // device [kMaxArchetypes][kMaxColumns]
     uint8_t exportedMask[kMaxArchetypes][kMaxColumns] = {};
@@ -68,6 +69,51 @@ struct SortParams {
     int32_t maxTiles;
     int32_t hasExported;
 };
+
+// ---- TMA (bulk async copy) staging of contiguous tiles: global -> shared memory by the
+// copy engine, completion through an mbarrier transaction count.  One elected thread
+// issues, everybody waits on the barrier phase.
+__device__ __forceinline__ uint32_t smemAddr(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbarInit(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbarExpectTx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_LOOP;\n"
+        "}\n" :: "r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+
+// global -> shared, bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void tmaLoad1D(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                          unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smemAddr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+
+// generic-proxy writes to shared memory must be ordered before the async proxy reuses it
+__device__ __forceinline__ void fenceProxyAsync()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 __device__ __forceinline__ bool sortActive(const SortParams &p, const TableDesc &t)
 {
@@ -147,16 +193,23 @@ sortOnesweepKernel(SortParams p, int pass)
     const int32_t *idx_in = p.idx[(pass + 1) & 1];
     uint32_t *keys_out = p.keys[pass & 1];
     int32_t *idx_out = p.idx[pass & 1];
-    uint32_t *lookback = p.lookback + (size_t)pass * p.maxTiles * 256;
+    uint32_t *lookback = p.lookback + (size_t)pass * 256;
+    constexpr size_t kTileStride = (size_t)kMaxPasses * 256;
     const int shift = 8 * pass;
 
     __shared__ uint32_t warp_hist[kSortWarps][256];
     __shared__ uint32_t digit_base[256];
     __shared__ uint32_t scan_tmp[kSortWarps];
     __shared__ uint32_t tile_digit_start[256];
-    __shared__ uint32_t stage_keys[kTileItems];
-    __shared__ int32_t stage_idx[kTileItems];
+    __shared__ __align__(128) uint32_t stage_keys[kTileItems];
+    __shared__ __align__(128) int32_t stage_idx[kTileItems];
+    __shared__ __align__(8) unsigned long long tile_bar;
     __shared__ int32_t tile_s;
+    if (threadIdx.x == 0) mbarInit(&tile_bar, 1);
+    uint32_t tile_phase = 0;
+    // the (key, index) tile of a pass is contiguous: whole tiles are staged by TMA;
+    // pass 0 reads the key column itself (contiguous when it is 4 bytes wide)
+    const bool key_col_dense = t.columnBytes[p.keyCol] == 4;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -190,13 +243,35 @@ sortOnesweepKernel(SortParams p, int pass)
         int32_t idx[kItemsPerThread];
         uint32_t rank[kItemsPerThread];
         const int32_t strip = tile * kTileItems + warp * (32 * kItemsPerThread);
+        const bool whole_tile = (tile + 1) * kTileItems <= n;
+        const bool staged = whole_tile && (pass > 0 || key_col_dense);
+        if (staged) {
+            if (threadIdx.x == 0) {
+                fenceProxyAsync();      // the previous tile's digit-order staging wrote these buffers
+                const uint32_t bytes = kTileItems * 4;
+                mbarExpectTx(&tile_bar, pass == 0 ? bytes : 2 * bytes);
+                if (pass == 0) {
+                    tmaLoad1D(stage_keys, (const uint32_t *)t.columns[p.keyCol] + (size_t)tile * kTileItems, bytes,
+                              &tile_bar);
+                } else {
+                    tmaLoad1D(stage_keys, keys_in + (size_t)tile * kTileItems, bytes, &tile_bar);
+                    tmaLoad1D(stage_idx, idx_in + (size_t)tile * kTileItems, bytes, &tile_bar);
+                }
+            }
+            mbarWait(&tile_bar, tile_phase);
+            tile_phase ^= 1u;
+        }
 #pragma unroll
         for (int r = 0; r < kItemsPerThread; r++) {
             const int32_t i = strip + r * 32 + lane;
             const bool valid = i < n;
             uint32_t k = 0;
             int32_t src = i;
-            if (valid) {
+            if (staged) {
+                const int local = warp * (32 * kItemsPerThread) + r * 32 + lane;
+                k = stage_keys[local];
+                if (pass > 0) src = stage_idx[local];
+            } else if (valid) {
                 if (pass == 0) {
                     k = loadKey(t, p.keyCol, i);
                 } else {
@@ -235,17 +310,17 @@ sortOnesweepKernel(SortParams p, int pass)
         if (tile == 0) {
             lb[d] = kFlagInclusive | tile_count;
         } else {
-            lb[(size_t)tile * 256 + d] = kFlagAggregate | tile_count;
+            lb[(size_t)tile * kTileStride + d] = kFlagAggregate | tile_count;
             __threadfence();
             int32_t look = tile - 1;
             while (true) {
-                uint32_t v = lb[(size_t)look * 256 + d];
+                uint32_t v = lb[(size_t)look * kTileStride + d];
                 if ((v >> 30) == 0) continue;     // predecessor not published yet
                 excl += v & kValueMask;
                 if ((v >> 30) == 2u) break;
                 look--;
             }
-            lb[(size_t)tile * 256 + d] = kFlagInclusive | (excl + tile_count);
+            lb[(size_t)tile * kTileStride + d] = kFlagInclusive | (excl + tile_count);
         }
         // -- the tile's own digit offsets (exclusive scan of tile_count over the 256 digits)
         {
@@ -334,17 +409,17 @@ sortRearrangeKernel(SortParams p)
     const int32_t *perm = p.idx[last];
     const uint32_t *sorted_keys = p.keys[last];
 
-    __shared__ int32_t perm_s[kRearrangeTile];
+    __shared__ __align__(128) int32_t perm_s[kRearrangeTile];
+    __shared__ __align__(8) unsigned long long perm_bar;
+    if (threadIdx.x == 0) mbarInit(&perm_bar, 1);
+    uint32_t perm_phase = 0;
 
     // scratch of the finished radix passes: wiped here, spread over all blocks
     {
         const int64_t tiles = (n + kTileItems - 1) / kTileItems;
         const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
-        for (int pass = 0; pass < p.numPasses; pass++) {
-            uint32_t *lb = p.lookback + (size_t)pass * p.maxTiles * 256;
-            for (int64_t i = gtid; i < tiles * 256; i += gstride) lb[i] = 0;
-        }
+        for (int64_t i = gtid; i < tiles * kMaxPasses * 256; i += gstride) p.lookback[i] = 0;
         for (int64_t i = gtid; i < p.numPasses * 256; i += gstride) p.bins[i] = 0;
     }
 
@@ -353,8 +428,18 @@ sortRearrangeKernel(SortParams p)
         const int32_t row0 = tile * kRearrangeTile;
         const int32_t rows = min(kRearrangeTile, new_n - row0);
         __syncthreads();
-        for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
-        __syncthreads();
+        if (rows == kRearrangeTile) {
+            // the tile's slice of the permutation: one bulk copy
+            if (threadIdx.x == 0) {
+                mbarExpectTx(&perm_bar, kRearrangeTile * 4);
+                tmaLoad1D(perm_s, perm + row0, kRearrangeTile * 4, &perm_bar);
+            }
+            mbarWait(&perm_bar, perm_phase);
+            perm_phase ^= 1u;
+        } else {
+            for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
+            __syncthreads();
+        }
 
         for (int32_t col = 0; col < t.numColumns; col++) {
             const void *src = t.columns[col];
@@ -445,10 +530,11 @@ sortCopyBackKernel(SortParams p, unsigned long long exported_mask)
     const int32_t col = blockIdx.y;
     if (col < t.numColumns && ((exported_mask >> col) & 1ull)) {
         // after the flip: t.columns[col] = twin (holds data), p.alt[col] = exported address
-        const uint32_t *src = (const uint32_t *)t.columns[col];
-        uint32_t *dst = (uint32_t *)p.alt[col];
-        const int64_t words = ((int64_t)n * t.columnBytes[col] + 3) / 4;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+        // (columns are 256-byte aligned with 256 bytes of slack: whole 16-byte units)
+        const uint4 *src = (const uint4 *)t.columns[col];
+        uint4 *dst = (uint4 *)p.alt[col];
+        const int64_t units = ((int64_t)n * t.columnBytes[col] + 15) / 16;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < units;
              i += (int64_t)gridDim.x * blockDim.x) {
             dst[i] = src[i];
         }
@@ -489,8 +575,6 @@ bool sortScratchCreate(Executor *ex, std::string *err)
         if (S.archetypes[a].registered && !S.tables[a].isSingleton)
             max_cap = std::max(max_cap, S.tables[a].capacity);
     }
-    sc->maxCapacity = max_cap;
-    sc->maxTiles = (max_cap + kTileItems - 1) / kTileItems + 1;
 
     auto alloc = [&](void **p, size_t bytes) {
         if (cudaMalloc(p, bytes) != cudaSuccess) return false;
@@ -498,13 +582,20 @@ bool sortScratchCreate(Executor *ex, std::string *err)
         cudaMemsetAsync(*p, 0, bytes, ex->stream);
         return true;
     };
+    // key / index / look-back scratch: address ranges big enough for any table, memory
+    // mapped for the largest table that exists (sortScratchEnsure maps more)
+    const size_t max_rows = 0x7fffff00ull;
     bool ok = true;
-    for (int i = 0; i < 2; i++) {
-        ok = ok && alloc((void **)&sc->keys[i], sizeof(uint32_t) * (size_t)max_cap);
-        ok = ok && alloc((void **)&sc->idx[i], sizeof(int32_t) * (size_t)max_cap);
+    for (int i = 0; i < 2 && ok; i++) {
+        ok = vmReserve(ex->gpu, &sc->keyRanges[i], max_rows * 4, 4096, err) &&
+             vmReserve(ex->gpu, &sc->idxRanges[i], max_rows * 4, 4096, err);
+        sc->keys[i] = (uint32_t *)sc->keyRanges[i].base;
+        sc->idx[i] = (int32_t *)sc->idxRanges[i].base;
     }
+    ok = ok && vmReserve(ex->gpu, &sc->lookbackRange, (max_rows / kTileItems + 2) * kMaxPasses * 256 * 4, 4096, err);
+    sc->lookback = (uint32_t *)sc->lookbackRange.base;
+    if (!ok || !sortScratchEnsure(ex, max_cap, err)) return false;
     ok = ok && alloc((void **)&sc->bins, sizeof(int32_t) * kMaxPasses * 256);
-    ok = ok && alloc((void **)&sc->lookback, sizeof(uint32_t) * (size_t)kMaxPasses * sc->maxTiles * 256);
     ok = ok && alloc((void **)&sc->ctrl, sizeof(SortCtrl));
     ok = ok && alloc((void **)&sc->altColumns, sizeof(void *) * kMaxArchetypes * kMaxColumns);
     if (!ok) {
@@ -525,9 +616,16 @@ bool sortScratchCreate(Executor *ex, std::string *err)
     for (uint32_t a = 0; a < S.numArchetypes; a++) {
         if (!S.archetypes[a].registered || S.tables[a].isSingleton) continue;
         const TableDesc &t = S.tables[a];
+        const bool growable = !ex->columnRanges[a].empty();
+        if (growable) ex->twinRanges[a].resize(t.numColumns);
         for (int32_t c = 0; c < t.numColumns; c++) {
             void *p = nullptr;
-            if (!alloc(&p, (size_t)t.columnBytes[c] * t.capacity + 256)) {
+            if (growable) {
+                // same address-range size as the column itself
+                if (!vmReserve(ex->gpu, &ex->twinRanges[a][c], ex->columnRanges[a][c].reserved,
+                               (size_t)t.columnBytes[c] * t.capacity + 256, err)) return false;
+                p = ex->twinRanges[a][c].base;
+            } else if (!alloc(&p, (size_t)t.columnBytes[c] * t.capacity + 256)) {
                 *err = "sort twin buffer allocation failed";
                 return false;
             }
@@ -540,9 +638,32 @@ bool sortScratchCreate(Executor *ex, std::string *err)
     return true;
 }
 
+bool sortScratchEnsure(Executor *ex, int32_t max_rows, std::string *err)
+{
+    SortScratch *sc = ex->sortScratch;
+    if (max_rows <= sc->maxCapacity) return true;
+    const size_t tiles = (size_t)(max_rows + kTileItems - 1) / kTileItems + 1;
+    for (int i = 0; i < 2; i++) {
+        if (!vmGrow(ex->gpu, &sc->keyRanges[i], (size_t)max_rows * 4, err) ||
+            !vmGrow(ex->gpu, &sc->idxRanges[i], (size_t)max_rows * 4, err)) return false;
+    }
+    if (!vmGrow(ex->gpu, &sc->lookbackRange, tiles * kMaxPasses * 256 * 4, err)) return false;
+    sc->maxCapacity = max_rows;
+    sc->maxTiles = (int32_t)tiles;
+    return true;
+}
+
 void sortScratchDestroy(Executor *ex)
 {
-    delete ex->sortScratch;
+    SortScratch *sc = ex->sortScratch;
+    if (sc) {
+        for (int i = 0; i < 2; i++) {
+            vmRelease(&sc->keyRanges[i]);
+            vmRelease(&sc->idxRanges[i]);
+        }
+        vmRelease(&sc->lookbackRange);
+    }
+    delete sc;
     ex->sortScratch = nullptr;
 }
 
@@ -606,7 +727,7 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
     const int rtiles = (t.capacity + kRearrangeTile - 1) / kRearrangeTile;
     const int rblocks = std::max(1, std::min(rtiles, ex->numSMs * 4));
     launchK(sortRearrangeKernel, dim3(rblocks), dim3(256), 0, s, p);
-    const int row_blocks = std::max(1, std::min((t.capacity + 255) / 256, ex->numSMs * 2));
+    const int row_blocks = std::max(1, std::min((t.capacity + 255) / 256, ex->numSMs * 4));
     dim3 rgrid((unsigned)row_blocks, (unsigned)t.numColumns);
 
     if (mask) launchK(sortCopyBackKernel, dim3(rgrid), dim3(256), 0, s, p, mask);

@@ -34,6 +34,7 @@ def test_dynamic_table_overflow_is_reported_at_the_reset_step(monkeypatch):
     # room: 31 rows / world at rest, 46 while a reset has destroyed-but-uncompacted cubes
     from sims import make_executor
     monkeypatch.setenv("MADRONA_B200_ROWS_PER_WORLD", "36")
+    monkeypatch.setenv("MADRONA_B200_TABLE_GROWTH", "0")     # growth off: the raw capacity cliff
     W = 64
     ex = make_executor("room", W, episode_len=6, seed=1)
     graph = ex.buildLaunchGraphAllTaskGraphs()
@@ -50,6 +51,7 @@ def test_table_overflow_during_world_construction(monkeypatch):
     import madrona_b200 as mb
     from sims import make_executor
     monkeypatch.setenv("MADRONA_B200_ROWS_PER_WORLD", "4")
+    monkeypatch.setenv("MADRONA_B200_TABLE_GROWTH", "0")
     with pytest.raises(mb.MadronaB200Error, match="table overflow"):
         make_executor("gridworld", 512, grid_size=6, episode_len=20, init_items=20, seed=0)
     _device_still_healthy()
@@ -96,4 +98,43 @@ def test_hull_vertex_cap():
     step, msg = _run_until_error(ex, graph, 40, {"action": ins["action"]}, {"action": act})
     assert step is not None and "physics buffer overflow" in msg, (step, msg)
     _device_still_healthy()
+    ex.close()
+
+
+# ---- table growth (role of the reference's VM-backed tables, src/mw/device/state.cpp:29-80) ----
+
+@pytest.mark.gpu
+def test_tables_grow_during_world_construction(monkeypatch):
+    # 4 rows / world of initial capacity, 20 items / world to create: construction must
+    # double the table until the worlds fit, and the run must equal the golden trace
+    from trace_utils import assert_traces_equal, load_golden, rollout_gpu
+    monkeypatch.setenv("MADRONA_B200_ROWS_PER_WORLD", "4")
+    W, steps, ins, outs = load_golden("gridworld_w5_s400")
+    got, _ = rollout_gpu("gridworld", W, 150, {k: v[:150] for k, v in ins.items()},
+                         {"grid_size": 3, "episode_len": 97, "init_items": 20, "seed": 3})
+    assert_traces_equal(got, {k: v[:151] for k, v in outs.items()})
+
+
+@pytest.mark.gpu
+def test_tables_grow_between_steps(monkeypatch):
+    # room: 31 body rows / world at rest, 46 while a reset waits for compaction; with 36
+    # rows / world to start with, the table must have been grown (between steps, from the
+    # high-water mark) before the reset at step 100 -- results unchanged, exported pointers stable
+    from sims import make_executor
+    from trace_utils import load_golden
+    import torch
+    monkeypatch.setenv("MADRONA_B200_ROWS_PER_WORLD", "36")
+    W, steps, ins, outs = load_golden("room_w4_s210")
+    ex = make_executor("room", W, episode_len=100, seed=21)
+    graph = ex.buildLaunchGraphAllTaskGraphs()
+    ptr_before = ex.getExported(9)
+    act, reset = ex.tensor(1, "int32", (W, 2, 3)), ex.tensor(0, "int32", (W, 1))
+    for t in range(120):
+        act.copy_(torch.from_numpy(np.ascontiguousarray(ins["action"][t])))
+        reset.copy_(torch.from_numpy(np.ascontiguousarray(ins["reset"][t])))
+        ex.run(graph)
+        rows = ex.exportedNumRows(9)
+        pos = ex.tensor(9, "float32", (rows, 3)).cpu().numpy()
+        assert np.array_equal(pos.view(np.uint32), outs["body_pos"][t + 1].view(np.uint32)), t
+    assert ex.getExported(9) == ptr_before
     ex.close()
