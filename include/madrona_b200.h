@@ -212,6 +212,60 @@ int64_t mb2_profile_nodes(mb2_executor *exec, const uint32_t *taskgraph_ids,
                           uint32_t num_taskgraphs, uint32_t reps,
                           char *json_out, uint64_t json_capacity);
 
+/* ---- physics assets --------------------------------------
+ * Role of RigidBodyAssets::processRigidBodyAssets (include/madrona/
+ * physics_assets.hpp:11-66, src/physics/physics_assets.cpp:1268-1407, with
+ * build_convex_hulls = false) + PhysicsLoader::loadRigidBodies /
+ * getObjectManager (include/madrona/physics_loader.hpp): convex hull meshes
+ * (polygon faces, coplanar faces merged) and collision objects in, the
+ * phys::ObjectManager a simulator's Config points at out -- half-edge meshes,
+ * Newell face planes, primitive / object AABBs, mass properties with the
+ * inertia tensor diagonalised -- on the host and, for gpu_id >= 0, on the GPU.
+ * Primitive types: 1 sphere, 2 hull, 4 plane (CollisionPrimitive::Type). */
+typedef struct mb2_source_hull {        /* == imp::SourceMesh as physics uses it */
+    const float *positions;             /* xyz per vertex */
+    uint32_t num_vertices;
+    const uint32_t *indices;            /* concatenated face loops */
+    const uint32_t *face_counts;        /* vertices per face; NULL: triangles */
+    uint32_t num_faces;
+} mb2_source_hull;
+typedef struct mb2_source_prim {        /* == phys::SourceCollisionPrimitive */
+    uint32_t type;
+    float sphere_radius;
+    uint32_t hull_idx;
+} mb2_source_prim;
+typedef struct mb2_source_object {      /* == phys::SourceCollisionObject */
+    const mb2_source_prim *prims;
+    uint32_t num_prims;
+    float inv_mass;
+    float mu_s, mu_d;
+} mb2_source_object;
+typedef struct mb2_object_manager mb2_object_manager;
+mb2_object_manager *mb2_process_rigid_body_assets(const mb2_source_hull *hulls, uint32_t num_hulls,
+                                                  const mb2_source_object *objects, uint32_t num_objects,
+                                                  int gpu_id);
+/* phys::ObjectManager * valid on the device (device != 0: what goes into the
+ * simulator's Config) or on the host */
+void *mb2_object_manager_ptr(const mb2_object_manager *mgr, int device);
+/* == phys::RigidBodyAssets (physics_assets.hpp:30-56): the host arrays behind the
+ * manager (hull arrays concatenated over hulls; primitives hold host pointers) */
+typedef struct mb2_rigid_body_assets {
+    void *half_edges;               /* geo::HalfEdge {next, rootVertex, face} */
+    uint32_t *face_base_half_edges;
+    void *face_planes;              /* geo::Plane {normal, d} */
+    void *vertices;                 /* math::Vector3 */
+    uint32_t num_half_edges, num_faces, num_verts;
+    void *primitives;               /* phys::CollisionPrimitive (56 B) */
+    void *primitive_aabbs;          /* math::AABB */
+    void *metadatas;                /* phys::RigidBodyMetadata (52 B) */
+    void *obj_aabbs;
+    uint32_t *prim_offsets;
+    uint32_t *prim_counts;
+    uint32_t num_convex_hulls, total_num_primitives, num_objs;
+} mb2_rigid_body_assets;
+void mb2_object_manager_host_assets(const mb2_object_manager *mgr, mb2_rigid_body_assets *out);
+void mb2_object_manager_destroy(mb2_object_manager *mgr);
+
 /* ---- multi-GPU gather of exported columns ------------------
  * No reference counterpart (the reference is single-GPU, mw_gpu.hpp:122):
  * worlds shard across GPUs, one process per GPU, and the only exchange is the

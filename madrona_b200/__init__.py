@@ -17,6 +17,10 @@ from .executor import (  # noqa: F401
     library_path,
     precompile,
     MeshBVHData,
+    RigidBodyAssets,
     PeerGather,
 )
-from .tensor import Tensor, TensorElementType  # noqa: F401
+from .tensor import (  # noqa: F401
+    Tensor, TensorElementType, NamedTensor, TrainInterface, TrainStepInputInterface,
+    TrainStepOutputInterface, TrainCheckpointingInterface,
+)

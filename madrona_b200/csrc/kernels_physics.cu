@@ -813,6 +813,51 @@ __device__ __forceinline__ void rowIntegrate(const EngineState &S, const Physics
     }
 }
 
+// ---- TGS (src/physics/tgs.cpp): the reference's solver skeleton integrates and nothing else
+__device__ __forceinline__ void rowTGSVelocities(const EngineState &S, const PhysicsState &P, const BodyArchetype &b, const i32 row, const i32 w)
+{
+    const u32 resp = bodyCol<u32>(S, b, PCResponseType, row);
+    if (resp == kRespStatic) return;
+    PVelocity &vel_ref = bodyCol<PVelocity>(S, b, PCVelocity, row);
+    const PVelocity vel = loadPairs(&vel_ref);
+    Vector3 v = vel.linear;
+    Vector3 omega = vel.angular;
+    const Quat q = loadQuat(&bodyCol<Quat>(S, b, PCRotation, row));
+    const PhysicsWorldParams &params = worldParams(S, P, w);
+    const PObjectManager &objs = worldObjects(S, P, w);
+    const PMetadata &meta = objs.metadata[bodyCol<i32>(S, b, PCObjectID, row)];
+    const float inv_m = meta.invMass;
+    const Vector3 inv_I = meta.invInertia;
+    const float h = params.h;
+    const Vector3 g { params.g.x, params.g.y, params.g.z };
+    if (resp == kRespDynamic) v += h * g;
+    v += h * inv_m * bodyCol<Vector3>(S, b, PCExtForce, row);
+    const Vector3 I { inv_I.x == 0 ? 0.0f : 1.0f / inv_I.x,
+                      inv_I.y == 0 ? 0.0f : 1.0f / inv_I.y,
+                      inv_I.z == 0 ? 0.0f : 1.0f / inv_I.z };
+    const Quat to_local = q.inv();
+    const Vector3 tau_local = to_local.rotateVec(bodyCol<Vector3>(S, b, PCExtTorque, row));
+    Vector3 omega_local = to_local.rotateVec(omega);
+    // NB: the reference multiplies I by the WORLD-space omega here (tgs.cpp:133-134)
+    omega_local += h * mulDiag(inv_I, tau_local - cross(omega_local, mulDiag(I, omega)));
+    omega = q.rotateVec(omega_local);
+    storePairs(&vel_ref, PVelocity { v, omega });
+}
+
+__device__ __forceinline__ void rowTGSPositions(const EngineState &S, const PhysicsState &P, const BodyArchetype &b, const i32 row, const i32 w)
+{
+    const float h = worldParams(S, P, w).h;
+    Vector3 x = bodyCol<Vector3>(S, b, PCPosition, row);
+    Quat q = loadQuat(&bodyCol<Quat>(S, b, PCRotation, row));
+    const PVelocity vel = loadPairs(&bodyCol<PVelocity>(S, b, PCVelocity, row));
+    x += h * vel.linear;
+    const Quat spin = Quat::fromAngularVec(0.5f * h * vel.angular);
+    q += spin * q;
+    q = q.normalize();
+    bodyCol<Vector3>(S, b, PCPosition, row) = x;
+    storeQuat(&bodyCol<Quat>(S, b, PCRotation, row), q);
+}
+
 __device__ __forceinline__ void rowSetVelocity(const EngineState &S, const PhysicsState &P, const BodyArchetype &b, const i32 row, const i32 w)
 {
     {
@@ -2331,6 +2376,7 @@ enum PhysPhase : u32 {
     PhaseUpdateLeaves = 1, PhaseRebuild, PhaseRefit, PhaseFindCandidates, PhaseIntegrate,
     PhaseNarrowphase, PhaseSolvePositions, PhaseSetVelocities, PhaseSolveVelocities,
     PhaseNarrowphaseSpheres,      // narrowphase incl. the sphere - hull (GJK) path
+    PhaseTGSVelocities, PhaseTGSPositions,
 };
 
 template <u32 OP>
@@ -2358,6 +2404,8 @@ physBodyKernel(EngineState *Sp)
         else if constexpr (OP == PhaseRefit) rowRefit(S, P, b, row, w);
         else if constexpr (OP == PhaseIntegrate) rowIntegrate(S, P, b, row, w);
         else if constexpr (OP == PhaseSetVelocities) rowSetVelocity(S, P, b, row, w);
+        else if constexpr (OP == PhaseTGSVelocities) rowTGSVelocities(S, P, b, row, w);
+        else if constexpr (OP == PhaseTGSPositions) rowTGSPositions(S, P, b, row, w);
     }
 }
 
@@ -2426,6 +2474,9 @@ physWorldKernel(EngineState *Sp)
         const i32 w = (i32)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
         if (w >= (i32)S.numWorlds) return;
         if constexpr (OP == PhaseFindCandidates) {
+            // a new step: the hull - hull queue starts empty (solvers that never run the
+            // position solve -- TGS -- would otherwise let it grow)
+            if (blockIdx.x == 0 && threadIdx.x == 0) *P.hullQueueCount = 0;
             __shared__ CandidateScratch cand_scratch;
             phaseFindCandidates(S, P, w, lane, warp, cand_scratch);
         }
@@ -2477,7 +2528,9 @@ bool physicsHostAfterRegistry(Executor *ex, const mb2_render_config *, std::stri
         bool all = true;
         for (int pc = 0; pc < PCCount; pc++) {
             int col = S.columnLookup[a][P.componentIDs[pc]];
-            if (col < 0) { all = false; break; }
+            // TGS keeps no per-body solver state (its RigidBody bundle ends at ExternalTorque)
+            const bool solver_state = pc == PCPrevState || pc == PCPreSolvePos || pc == PCPreSolveVel;
+            if (col < 0 && !(solver_state && P.solver == 1u)) { all = false; break; }
             b.cols[pc] = col;
         }
         if (!all) continue;
@@ -2586,6 +2639,12 @@ bool physicsEnqueueNodes(Executor *ex, const NodeRecord *recs, uint32_t count, c
         case NodePhysSolvePositions:
             launchK(physWorldKernel<PhaseSolvePositions>, dim3(sgrid), dim3(wblock), 0, s, d);
             break;
+        case NodePhysTGSVelocities:
+            launchK(physBodyKernel<PhaseTGSVelocities>, dim3(bgrid), dim3(256), 0, s, d);
+            break;
+        case NodePhysTGSPositions:
+            launchK(physBodyKernel<PhaseTGSPositions>, dim3(bgrid), dim3(256), 0, s, d);
+            break;
         case NodePhysSetVelocities:
             launchK(physBodyKernel<PhaseSetVelocities>, dim3(bgrid), dim3(256), 0, s, d);
             break;
@@ -2639,6 +2698,8 @@ uint64_t physicsNodeBytes(Executor *ex, const NodeRecord &rec, const char **name
     }
     case NodePhysSolvePositions: *name = "phys_solve_positions"; *rows = total(P.contactCounts);
         return 368ull * (*rows);
+    case NodePhysTGSVelocities: *name = "phys_tgs_velocities"; *rows = bodies; return 104ull * bodies;
+    case NodePhysTGSPositions: *name = "phys_tgs_positions"; *rows = bodies; return 80ull * bodies;
     case NodePhysSetVelocities: *name = "phys_set_velocities"; *rows = bodies; return 80ull * bodies;
     case NodePhysSolveVelocities: *name = "phys_solve_velocities"; *rows = total(P.contactCounts);
         return 360ull * (*rows);

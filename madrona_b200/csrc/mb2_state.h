@@ -125,6 +125,8 @@ enum NodeKind : u32 {
     NodePhysSolveVelocities = 23,
     NodePhysClearContacts = 24,
     NodePhysClearCandidates = 25,
+    NodePhysTGSVelocities = 26,    // tgs::integrateVelocities (src/physics/tgs.cpp:92-142)
+    NodePhysTGSPositions = 27,     // tgs::integratePositions (tgs.cpp:171-195)
     NodeRenderPrepare = 32,
 };
 

@@ -202,6 +202,16 @@ struct XPBDRigidBodyState : Bundle<
 
 struct Joint : Archetype<JointConstraint> {};
 
+}
+
+namespace tgs {
+// == tgs.cpp:15-18
+struct TGSRigidBodyState : Bundle<
+> {};
+}
+
+namespace xpbd {
+
 // The reference keeps its contact / joint queries in this singleton
 // (xpbd.cpp:20-23).  The engine does not need it, but registering it keeps the
 // number and order of singleton archetypes -- and therefore every entity ID
@@ -239,22 +249,25 @@ inline void registerTypes(ECSRegistry &registry, Solver solver = Solver::XPBD)
     registry.registerSingleton<PhysicsSystemState>();
     registry.registerSingleton<ObjectData>();
 
+    // solver state: xpbd::registerTypes (xpbd.cpp:1055-1069) / tgs::registerTypes
+    // (tgs.cpp:28-43).  TGS keeps no per-body state: its bundle is empty.
     registry.registerComponent<xpbd::SubstepPrevState>();
     registry.registerComponent<xpbd::PreSolvePositional>();
     registry.registerComponent<xpbd::PreSolveVelocity>();
     registry.registerArchetype<xpbd::Joint>();
     registry.registerSingleton<xpbd::SolverState>();
-    registry.registerBundle<xpbd::XPBDRigidBodyState>();
-    registry.registerBundleAlias<SolverBundleAlias, xpbd::XPBDRigidBodyState>();
+    if (solver == Solver::TGS) {
+        registry.registerBundle<tgs::TGSRigidBodyState>();
+        registry.registerBundleAlias<SolverBundleAlias, tgs::TGSRigidBodyState>();
+    } else {
+        registry.registerBundle<xpbd::XPBDRigidBodyState>();
+        registry.registerBundleAlias<SolverBundleAlias, xpbd::XPBDRigidBodyState>();
+    }
 
     registry.registerBundle<RigidBody>();
 
     // tell the engine which components / archetypes are the physics ones
     mb2::PhysicsState &P = *mwGPU::engine().physics;
-    if (solver != Solver::XPBD) {
-        // TGS (src/physics/tgs.cpp) is not part of this engine's scope
-        mwGPU::raiseError(mb2::ErrRegistry);
-    }
     P.solver = (uint32_t)solver;
     P.componentIDs[mb2::PCPosition] = TypeTracker::typeID<base::Position>();
     P.componentIDs[mb2::PCRotation] = TypeTracker::typeID<base::Rotation>();
@@ -411,9 +424,21 @@ inline TaskGraphNodeID setupBroadphaseTasks(TaskGraphBuilder &builder,
 inline TaskGraphNodeID setupPhysicsStepTasks(TaskGraphBuilder &builder,
                                              Span<const TaskGraphNodeID> deps,
                                              CountT num_substeps,
-                                             Solver = Solver::XPBD)
+                                             Solver solver = Solver::XPBD)
 {
     TaskGraphNodeID cur = mwGPU::pushBuiltin(builder, deps, mb2::NodePhysFindCandidates);
+    if (solver == Solver::TGS) {
+        // tgs::setupTGSSolverTasks (src/physics/tgs.cpp:213-302): the narrowphase runs once,
+        // then every substep integrates velocities and positions; the reference's contact /
+        // joint prepare, warm-start and solve systems are empty bodies there (:59-90,
+        // 144-205), so the solver is a collision-free integrator -- reproduced as it is.
+        cur = mwGPU::pushBuiltin(builder, { cur }, mb2::NodePhysNarrowphase);
+        for (CountT i = 0; i < num_substeps; i++) {
+            cur = mwGPU::pushBuiltin(builder, { cur }, mb2::NodePhysTGSVelocities);
+            cur = mwGPU::pushBuiltin(builder, { cur }, mb2::NodePhysTGSPositions);
+        }
+        return mwGPU::pushBuiltin(builder, { cur }, mb2::NodePhysBroadphaseUpdate, 0, 0, 0);
+    }
     for (CountT i = 0; i < num_substeps; i++) {
         cur = mwGPU::pushBuiltin(builder, { cur }, mb2::NodePhysSubstepBegin);
         cur = mwGPU::pushBuiltin(builder, { cur }, mb2::NodePhysNarrowphase);

@@ -42,6 +42,10 @@ EXPORTED_SYMBOLS = [
     "mb2_mesh_bvh_data_view",
     "mb2_mesh_bvh_triangle_sources",
     "mb2_mesh_bvh_data_destroy",
+    "mb2_process_rigid_body_assets",
+    "mb2_object_manager_ptr",
+    "mb2_object_manager_host_assets",
+    "mb2_object_manager_destroy",
     "mb2_render_debug_hits",
     "mb2_render_debug_buffer",
     "mb2_peer_gather_create",
@@ -108,6 +112,33 @@ class _RenderConfigC(ctypes.Structure):      # == madrona::CudaBatchRenderConfig
         ("near_plane", ctypes.c_float),
         ("far_plane", ctypes.c_float),
     ]
+
+
+class _SourceHullC(ctypes.Structure):
+    _fields_ = [("positions", ctypes.c_void_p), ("num_vertices", ctypes.c_uint32),
+                ("indices", ctypes.c_void_p), ("face_counts", ctypes.c_void_p),
+                ("num_faces", ctypes.c_uint32)]
+
+
+class _SourcePrimC(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_uint32), ("sphere_radius", ctypes.c_float), ("hull_idx", ctypes.c_uint32)]
+
+
+class _SourceObjectC(ctypes.Structure):
+    _fields_ = [("prims", ctypes.POINTER(_SourcePrimC)), ("num_prims", ctypes.c_uint32),
+                ("inv_mass", ctypes.c_float), ("mu_s", ctypes.c_float), ("mu_d", ctypes.c_float)]
+
+
+class _RigidBodyAssetsC(ctypes.Structure):
+    _fields_ = [("half_edges", ctypes.c_void_p), ("face_base_half_edges", ctypes.c_void_p),
+                ("face_planes", ctypes.c_void_p), ("vertices", ctypes.c_void_p),
+                ("num_half_edges", ctypes.c_uint32), ("num_faces", ctypes.c_uint32),
+                ("num_verts", ctypes.c_uint32),
+                ("primitives", ctypes.c_void_p), ("primitive_aabbs", ctypes.c_void_p),
+                ("metadatas", ctypes.c_void_p), ("obj_aabbs", ctypes.c_void_p),
+                ("prim_offsets", ctypes.c_void_p), ("prim_counts", ctypes.c_void_p),
+                ("num_convex_hulls", ctypes.c_uint32), ("total_num_primitives", ctypes.c_uint32),
+                ("num_objs", ctypes.c_uint32)]
 
 
 class _MeshSourceC(ctypes.Structure):
@@ -184,6 +215,15 @@ def load_library() -> ctypes.CDLL:
     lib.mb2_mesh_bvh_triangle_sources.restype = ctypes.POINTER(ctypes.c_uint32)
     lib.mb2_mesh_bvh_data_destroy.argtypes = [vp]
     lib.mb2_mesh_bvh_data_destroy.restype = None
+    lib.mb2_process_rigid_body_assets.argtypes = [ctypes.POINTER(_SourceHullC), ctypes.c_uint32,
+                                                  ctypes.POINTER(_SourceObjectC), ctypes.c_uint32, ctypes.c_int]
+    lib.mb2_process_rigid_body_assets.restype = vp
+    lib.mb2_object_manager_ptr.argtypes = [vp, ctypes.c_int]
+    lib.mb2_object_manager_ptr.restype = vp
+    lib.mb2_object_manager_host_assets.argtypes = [vp, ctypes.POINTER(_RigidBodyAssetsC)]
+    lib.mb2_object_manager_host_assets.restype = None
+    lib.mb2_object_manager_destroy.argtypes = [vp]
+    lib.mb2_object_manager_destroy.restype = None
     lib.mb2_render_debug_hits.argtypes = [vp]
     lib.mb2_render_debug_hits.restype = vp
     lib.mb2_render_debug_buffer.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
@@ -491,6 +531,100 @@ class MeshBVHData:
     def close(self):
         if self._h:
             self._lib.mb2_mesh_bvh_data_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RigidBodyAssets:
+    """Physics asset pipeline (role of RigidBodyAssets::processRigidBodyAssets +
+    PhysicsLoader::loadRigidBodies, include/madrona/physics_assets.hpp:30-66): convex hull
+    meshes and collision objects in, a phys::ObjectManager out.
+
+    hulls:   list of (positions [nv,3] f32, faces) -- faces a list of CCW vertex loops
+    objects: list of dicts {"prims": [("sphere", r) | ("hull", idx) | ("plane",)],
+                            "inv_mass": float, "mu_s": float, "mu_d": float}
+    `device_ptr` is what a simulator's Config.rigidBodyObjectManager takes (gpu_id >= 0)."""
+
+    TYPES = {"sphere": 1, "hull": 2, "plane": 4}
+
+    def __init__(self, hulls, objects, gpu_id: int = -1):
+        import numpy as np
+        self._lib = load_library()
+        keep = []
+        c_hulls = (_SourceHullC * max(len(hulls), 1))()
+        for i, (pos, faces) in enumerate(hulls):
+            pos = np.ascontiguousarray(pos, dtype=np.float32)
+            counts = np.asarray([len(f) for f in faces], dtype=np.uint32)
+            idx = np.asarray([v for f in faces for v in f], dtype=np.uint32)
+            keep += [pos, counts, idx]
+            c_hulls[i] = _SourceHullC(pos.ctypes.data, len(pos), idx.ctypes.data, counts.ctypes.data, len(faces))
+        c_objs = (_SourceObjectC * max(len(objects), 1))()
+        for i, obj in enumerate(objects):
+            prims = (_SourcePrimC * len(obj["prims"]))()
+            for j, p in enumerate(obj["prims"]):
+                prims[j] = _SourcePrimC(self.TYPES[p[0]], float(p[1]) if p[0] == "sphere" else 0.0,
+                                        int(p[1]) if p[0] == "hull" else 0)
+            keep.append(prims)
+            c_objs[i] = _SourceObjectC(prims, len(obj["prims"]), float(obj["inv_mass"]),
+                                       float(obj.get("mu_s", 0.5)), float(obj.get("mu_d", 0.5)))
+        self._h = self._lib.mb2_process_rigid_body_assets(c_hulls, len(hulls), c_objs, len(objects), gpu_id)
+        if not self._h:
+            raise MadronaB200Error(_last_error(self._lib))
+        self.gpu_id = gpu_id
+
+    @property
+    def device_ptr(self) -> int:
+        p = self._lib.mb2_object_manager_ptr(self._h, 1)
+        if not p:
+            raise MadronaB200Error("RigidBodyAssets was built without a GPU (gpu_id < 0)")
+        return int(p)
+
+    def host_arrays(self) -> dict:
+        """Copies of the host arrays, pointers in the primitives replaced by element offsets
+        into the concatenated hull arrays."""
+        import numpy as np
+        v = _RigidBodyAssetsC()
+        self._lib.mb2_object_manager_host_assets(self._h, ctypes.byref(v))
+
+        def arr(ptr, n, width):
+            if n == 0:
+                return np.zeros((0, width), dtype=np.uint8)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(n, width)).copy()
+        prims_raw = arr(v.primitives, v.total_num_primitives, 56)
+        prims = []
+        for row in prims_raw:
+            type_ = int(row[0:4].view(np.uint32)[0])
+            if type_ == 1:
+                prims.append((type_, float(row[8:12].view(np.float32)[0])))
+            elif type_ == 2:
+                ptrs = row[8:40].view(np.uint64)
+                n = row[40:52].view(np.uint32)
+                prims.append((type_, (int(ptrs[0]) - v.half_edges) // 12, (int(ptrs[1]) - v.face_base_half_edges) // 4,
+                              (int(ptrs[3]) - v.vertices) // 12, int(n[0]), int(n[1]), int(n[2]),
+                              (int(ptrs[2]) - v.face_planes) // 16))
+            else:
+                prims.append((type_,))
+        return {
+            "half_edges": arr(v.half_edges, v.num_half_edges, 12).view(np.uint32),
+            "face_base": arr(v.face_base_half_edges, v.num_faces, 4).view(np.uint32).reshape(-1),
+            "planes": arr(v.face_planes, v.num_faces, 16).view(np.float32),
+            "vertices": arr(v.vertices, v.num_verts, 12).view(np.float32),
+            "prims": prims,
+            "prim_aabbs": arr(v.primitive_aabbs, v.total_num_primitives, 24).view(np.float32),
+            "metadatas": arr(v.metadatas, v.num_objs, 52).view(np.float32),
+            "obj_aabbs": arr(v.obj_aabbs, v.num_objs, 24).view(np.float32),
+            "prim_offsets": arr(v.prim_offsets, v.num_objs, 4).view(np.uint32).reshape(-1),
+            "prim_counts": arr(v.prim_counts, v.num_objs, 4).view(np.uint32).reshape(-1),
+        }
+
+    def close(self):
+        if self._h:
+            self._lib.mb2_object_manager_destroy(self._h)
             self._h = None
 
     def __del__(self):

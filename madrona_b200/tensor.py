@@ -108,3 +108,110 @@ class Tensor:
         if self.isOnGPU():
             return torch.as_tensor(self, device=f"cuda:{self._gpu_id}")
         return torch.from_numpy(self.to_numpy())
+
+
+# ---- madrona::py::TrainInterface (include/madrona/py/utils.hpp:143-201) ----------------------
+# What a simulator's Manager hands to a learner: named action tensors, resets and
+# simCtrl going in; observations, rewards, dones (+ stats / pbt) coming out.  The
+# reference's JAX bridge (src/python/bindings.cpp:80-283) turns these into XLA custom
+# calls; here the same structure is plain data plus the copy helpers, with torch
+# doing the device copies.
+
+from dataclasses import dataclass, field
+from typing import Dict, List
+
+
+@dataclass
+class NamedTensor:
+    name: str
+    tensor: Tensor
+
+
+@dataclass
+class TrainStepInputInterface:
+    actions: List[NamedTensor]
+    resets: Tensor
+    simCtrl: Optional[Tensor] = None
+    pbt: List[NamedTensor] = field(default_factory=list)
+
+
+@dataclass
+class TrainStepOutputInterface:
+    observations: List[NamedTensor]
+    rewards: Tensor
+    dones: Tensor
+    stats: List[NamedTensor] = field(default_factory=list)
+    pbt: List[NamedTensor] = field(default_factory=list)
+
+
+@dataclass
+class TrainCheckpointingInterface:
+    checkpointData: Tensor
+
+
+class TrainInterface:
+    """Mirror of madrona::py::TrainInterface: stepInputs() / stepOutputs() /
+    checkpointing(), and the copy helpers in the reference's buffer order
+    (src/python/utils.cpp: inputs = actions..., resets, simCtrl, pbt...; outputs =
+    observations..., rewards, dones, stats..., pbt...)."""
+
+    def __init__(self, step_inputs: TrainStepInputInterface, step_outputs: TrainStepOutputInterface,
+                 checkpointing: Optional[TrainCheckpointingInterface] = None):
+        self._in, self._out, self._ckpt = step_inputs, step_outputs, checkpointing
+
+    def stepInputs(self) -> TrainStepInputInterface:
+        return self._in
+
+    def stepOutputs(self) -> TrainStepOutputInterface:
+        return self._out
+
+    def checkpointing(self) -> Optional[TrainCheckpointingInterface]:
+        return self._ckpt
+
+    # -- ordered views (the order the reference's copy functions walk the buffers in)
+    def _input_tensors(self) -> List[Tensor]:
+        out = [nt.tensor for nt in self._in.actions] + [self._in.resets]
+        if self._in.simCtrl is not None:
+            out.append(self._in.simCtrl)
+        return out + [nt.tensor for nt in self._in.pbt]
+
+    def _observation_tensors(self) -> List[Tensor]:
+        return [nt.tensor for nt in self._out.observations]
+
+    def _output_tensors(self) -> List[Tensor]:
+        return (self._observation_tensors() + [self._out.rewards, self._out.dones] +
+                [nt.tensor for nt in self._out.stats] + [nt.tensor for nt in self._out.pbt])
+
+    def copyStepInputs(self, buffers) -> None:
+        """cpuCopyStepInputs / cudaCopyStepInputs: caller buffers -> the simulator's input tensors."""
+        import torch
+        for dst, src in zip(self._input_tensors(), buffers):
+            dst.to_torch().copy_(torch.as_tensor(src).reshape(dst.dims()), non_blocking=True)
+
+    def copyObservations(self, buffers) -> None:
+        for src, dst in zip(self._observation_tensors(), buffers):
+            dst.copy_(src.to_torch().reshape(dst.shape), non_blocking=True)
+
+    def copyStepOutputs(self, buffers) -> None:
+        """cpuCopyStepOutputs / cudaCopyStepOutputs: the simulator's outputs -> caller buffers."""
+        for src, dst in zip(self._output_tensors(), buffers):
+            dst.copy_(src.to_torch().reshape(dst.shape), non_blocking=True)
+
+    # -- the pytree view the reference's Python side works with (bindings.cpp:30-78)
+    def step_inputs(self) -> Dict[str, object]:
+        d = {"actions": {nt.name: nt.tensor.to_torch() for nt in self._in.actions},
+             "resets": self._in.resets.to_torch()}
+        if self._in.simCtrl is not None:
+            d["sim_ctrl"] = self._in.simCtrl.to_torch()
+        if self._in.pbt:
+            d["pbt"] = {nt.name: nt.tensor.to_torch() for nt in self._in.pbt}
+        return d
+
+    def step_outputs(self) -> Dict[str, object]:
+        d = {"obs": {nt.name: nt.tensor.to_torch() for nt in self._out.observations},
+             "rewards": self._out.rewards.to_torch(), "dones": self._out.dones.to_torch()}
+        if self._out.stats:
+            d["stats"] = {nt.name: nt.tensor.to_torch() for nt in self._out.stats}
+        if self._out.pbt:
+            d["pbt"] = {nt.name: nt.tensor.to_torch() for nt in self._out.pbt}
+        return d

@@ -149,6 +149,29 @@ SIMS: Dict[str, SimDesc] = {
         defaults={"episode_len": 100, "seed": 0},
         objects=_arena_objects,
     ),
+    # the room fixture with Solver::TGS (the reference's TGS is a collision-free integrator)
+    "room_tgs": SimDesc(
+        name="room_tgs",
+        sources=[os.path.join(_ROOT, "room", "sim.cpp")],
+        num_exports=13,
+        num_taskgraphs=1,
+        inputs=[Slot(0, "reset", "int32", (1,)), Slot(1, "action", "int32", (2, 3))],
+        outputs=[Slot(2, "reward", "float32", (2,)), Slot(3, "done", "int32", (2,)),
+                 Slot(4, "self_obs", "float32", (2, 9)), Slot(5, "lidar", "float32", (2, 16, 2)),
+                 Slot(6, "agent_pos", "float32", (2, 3)), Slot(7, "agent_rot", "float32", (2, 4)),
+                 Slot(8, "body_count", "int32", (1,)),
+                 Slot(9, "body_pos", "float32", (3,), dynamic=True),
+                 Slot(10, "body_rot", "float32", (4,), dynamic=True),
+                 Slot(11, "body_entity", "int32", (2,), dynamic=True),
+                 Slot(12, "body_vel", "float32", (6,), dynamic=True)],
+        pack_config=_room_cfg,
+        pack_init=_room_init,
+        oracle_extra=lambda cfg: [int(cfg["episode_len"]), int(cfg.get("seed", 0)),
+                                  int(cfg.get("grab_period", 0))],
+        defaults={"episode_len": 100, "seed": 0, "grab_period": 0},
+        objects=_room_objects,
+        compile_flags=["-DROOM_TGS=1"],
+    ),
     # the room fixture built with -DROOM_ENABLE_RENDER=1 (BASELINE configs[3]); GPU only:
     # the reference CPU backend cannot ray cast (src/render/ecs_system.cpp:684-689)
     "room_render": SimDesc(
@@ -271,19 +294,27 @@ def pack_world_inits(desc: SimDesc, num_worlds: int, cfg: Dict) -> bytes:
 
 def make_executor(name: str, num_worlds: int, gpu_id: int = 0, objects_fn=None, **cfg):
     """Build a madrona_b200.MWCudaExecutor for a fixture sim (needs a B200).
-    objects_fn overrides the fixture's ObjectManager blob (same object indices)."""
+    objects_fn overrides the fixture's ObjectManager (same object indices): it returns either
+    a (blob, relocations) pair or a madrona_b200.RigidBodyAssets built on this GPU."""
     import madrona_b200 as mb
 
     desc = SIMS[name]
     full = dict(desc.defaults)
     full.update(cfg)
     keep_alive = None
+    made = None
     if desc.objects is not None:
+        made = (objects_fn or desc.objects)()
+        if isinstance(made, mb.RigidBodyAssets):
+            full["obj_mgr_ptr"] = made.device_ptr
+            keep_alive = made
+            made = None
+    if made is not None:
         # upload the ObjectManager blob and relocate its pointers to device addresses
         import numpy as np
         import torch
         from .objects import relocate
-        blob, relocs = (objects_fn or desc.objects)()
+        blob, relocs = made
         dev_buf = torch.empty(len(blob) + 64, dtype=torch.uint8, device=f"cuda:{gpu_id}")
         base = (dev_buf.data_ptr() + 63) // 64 * 64
         fixed = relocate(blob, relocs, base)

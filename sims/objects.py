@@ -214,7 +214,7 @@ def hex_prism_half_edge_mesh():
     return build_half_edge_mesh(v, orient_faces(v, faces))
 
 
-def build_objects(specs) -> Tuple[bytes, List[int]]:
+def build_objects(specs, plane_extent: float = 1.0e5) -> Tuple[bytes, List[int]]:
     """specs: one dict per object -- {"mesh": <half-edge mesh dict> | "plane" | ("sphere", r),
     "meta": bytes(52)}; one primitive per object.  Same blob layout as room_objects()."""
     b = BlobBuilder()
@@ -229,7 +229,7 @@ def build_objects(specs) -> Tuple[bytes, List[int]]:
     prim_size = 56
     prims_off = b.add(b"\0" * (prim_size * n_obj), align=16)
     aabbs = b""
-    big = 1.0e5
+    big = plane_extent
     for i, sp in enumerate(specs):
         base = prims_off + i * prim_size
         m = sp["mesh"]

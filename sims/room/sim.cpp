@@ -17,11 +17,18 @@ constexpr float kLength = 30.f;        //        y in [0, 30]
 constexpr float kWallThick = 0.5f;
 constexpr float kWallHeight = 2.f;
 constexpr float kDoorWidth = 3.f;
+#ifdef ROOM_TGS
+// build variant: the reference's TGS solver selected through the same API (its contact /
+// joint solves are empty in the reference, src/physics/tgs.cpp: bodies fall freely)
+constexpr PhysicsSystem::Solver kSolver = PhysicsSystem::Solver::TGS;
+#else
+constexpr PhysicsSystem::Solver kSolver = PhysicsSystem::Solver::XPBD;
+#endif
 
 void Sim::registerTypes(ECSRegistry &registry, const Config &)
 {
     base::registerTypes(registry);
-    PhysicsSystem::registerTypes(registry);
+    PhysicsSystem::registerTypes(registry, kSolver);
 #ifdef ROOM_ENABLE_RENDER
     render::RenderingSystem::registerTypes(registry, nullptr);
 #endif
@@ -329,7 +336,7 @@ void Sim::setupTasks(TaskGraphManager &mgr, const Config &)
 
     auto broadphase = PhysicsSystem::setupBroadphaseTasks(builder, {move});
     auto physics = PhysicsSystem::setupPhysicsStepTasks(builder, {broadphase},
-                                                        kNumSubsteps);
+                                                        kNumSubsteps, kSolver);
 
     auto zero_vel = builder.addToGraph<ParallelForNode<Engine, agentZeroVelSystem,
         Velocity, Action>>({physics});
@@ -379,7 +386,7 @@ Sim::Sim(Engine &ctx, const Config &cfg, const WorldInit &init)
       joint(Entity::none())
 {
     PhysicsSystem::init(ctx, cfg.objMgr, kDeltaT, kNumSubsteps,
-                        -9.8f * math::up, kMaxBodies);
+                        -9.8f * math::up, kMaxBodies, kSolver);
 
     plane = ctx.makeEntity<PhysicsEntity>();
     for (int32_t i = 0; i < kNumBorderWalls; i++) {

@@ -33,6 +33,8 @@ CASES = [
     # Hide&Seek-class arena: wedge / hexagonal hulls, latched doors (fixed joints to static
     # walls), grab (fixed) and shove (one-step hinge) joints, two resets inside the trace
     ("arena_w2_s200", "arena", 2, 200, {"episode_len": 90, "seed": 17}),
+    # Solver::TGS through the same API (tgs.cpp: integrate velocities / positions only)
+    ("room_tgs_w3_s45", "room_tgs", 3, 45, {"episode_len": 30, "seed": 8}),
     # spheres: sphere-sphere, sphere-plane and sphere-hull (GJK) contacts
     ("balls_w6_s160", "balls", 6, 160, {"seed": 3}),
     # 95 bodies per world: candidate search beyond one 64-leaf mask word, ~300 contacts per world

@@ -54,3 +54,30 @@ def test_exported_column_as_tensor():
     assert view.device.type == "cuda" and tuple(view.shape) == (8, 1)
     assert view.data_ptr() == ex.getExported(0)
     ex.close()
+
+
+def test_train_interface_mirrors_reference_structure_and_buffer_order():
+    from madrona_b200 import (NamedTensor, TrainInterface, TrainStepInputInterface, TrainStepOutputInterface)
+    act = torch.zeros(4, 2, dtype=torch.int32)
+    resets = torch.zeros(4, 1, dtype=torch.int32)
+    obs_a = torch.arange(8, dtype=torch.float32).reshape(4, 2)
+    obs_b = torch.ones(4, 3)
+    rew, done = torch.full((4, 1), 0.5), torch.zeros(4, 1, dtype=torch.int32)
+    iface = TrainInterface(
+        TrainStepInputInterface(actions=[NamedTensor("move", Tensor.from_torch(act))], resets=Tensor.from_torch(resets)),
+        TrainStepOutputInterface(observations=[NamedTensor("self", Tensor.from_torch(obs_a)),
+                                               NamedTensor("lidar", Tensor.from_torch(obs_b))],
+                                 rewards=Tensor.from_torch(rew), dones=Tensor.from_torch(done)))
+    assert [nt.name for nt in iface.stepInputs().actions] == ["move"]
+    assert iface.checkpointing() is None
+    # inputs: actions..., resets (utils.hpp:149-154 order); zero copy into the sim's tensors
+    iface.copyStepInputs([torch.full((4, 2), 3, dtype=torch.int32), torch.ones(4, 1, dtype=torch.int32)])
+    assert (act == 3).all() and (resets == 1).all()
+    # outputs: observations..., rewards, dones (utils.hpp:156-162 order)
+    bufs = [torch.empty(4, 2), torch.empty(4, 3), torch.empty(4, 1), torch.empty(4, 1, dtype=torch.int32)]
+    iface.copyStepOutputs(bufs)
+    assert torch.equal(bufs[0], obs_a) and torch.equal(bufs[1], obs_b) and (bufs[2] == 0.5).all()
+    tree = iface.step_outputs()
+    assert set(tree) == {"obs", "rewards", "dones"} and set(tree["obs"]) == {"self", "lidar"}
+    assert tree["obs"]["self"].data_ptr() == obs_a.data_ptr()
+    assert iface.step_inputs()["actions"]["move"].data_ptr() == act.data_ptr()

@@ -24,7 +24,7 @@ def make_inputs(sim: str, num_worlds: int, num_steps: int, seed: int = 0) -> Dic
             "reset": (rng.random((num_steps, num_worlds, 1)) < 0.02).astype(np.int32),
             "action": rng.integers(0, 5, size=(num_steps, num_worlds, 2), dtype=np.int32),
         }
-    if sim == "room":
+    if sim in ("room", "room_tgs"):
         # mostly "full speed ahead" so agents reach cubes, walls and each other
         amount = np.where(rng.random((num_steps, num_worlds, 2)) < 0.7, 3,
                           rng.integers(0, 4, size=(num_steps, num_worlds, 2)))
