@@ -28,7 +28,10 @@ namespace mb2 {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItemsPerThread = 8;
+#ifndef MB2_SORT_ITEMS
+#define MB2_SORT_ITEMS 8
+#endif
+constexpr int kItemsPerThread = MB2_SORT_ITEMS;
 constexpr int kTileItems = kSortThreads * kItemsPerThread;   // 2048
 constexpr int kMaxPasses = 4;
 
