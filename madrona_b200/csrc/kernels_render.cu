@@ -249,58 +249,12 @@ __device__ __forceinline__ RayShear rayShear(Vector3 d, Diag3x3 inv_d)
     int kz = (ax > ay && ax > az) ? 0 : (ay > az ? 1 : 2);
     int kx = kz + 1 == 3 ? 0 : kz + 1;
     int ky = kx + 1 == 3 ? 0 : kx + 1;
-    if (d[kz] < 0.f) {
+    auto pick = [](int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); };
+    if (pick(kz, d.x, d.y, d.z) < 0.f) {
         int t = kx; kx = ky; ky = t;
     }
-    return RayShear { kx, ky, kz, d[kx] * inv_d[kz], d[ky] * inv_d[kz], inv_d[kz] };
-}
-
-__device__ __forceinline__ bool rayTriangle(Vector3 a, Vector3 b, Vector3 c, const RayShear &rs,
-                                            Vector3 org, float t_max, float *out_t, Vector3 *out_n)
-{
-    const Vector3 A = a - org, B = b - org, C = c - org;
-    const float a_kz = A[rs.kz], a_kx = A[rs.kx], a_ky = A[rs.ky];
-    const float b_kz = B[rs.kz], b_kx = B[rs.kx], b_ky = B[rs.ky];
-    const float c_kz = C[rs.kz], c_kx = C[rs.kx], c_ky = C[rs.ky];
-
-    const float Ax = fmaf(-rs.Sx, a_kz, a_kx), Ay = fmaf(-rs.Sy, a_kz, a_ky);
-    const float Bx = fmaf(-rs.Sx, b_kz, b_kx), By = fmaf(-rs.Sy, b_kz, b_ky);
-    const float Cx = fmaf(-rs.Sx, c_kz, c_kx), Cy = fmaf(-rs.Sy, c_kz, c_ky);
-
-    float U = fmaf(Cx, By, -Cy * Bx);
-    float V = fmaf(Ax, Cy, -Ay * Cx);
-    float W = fmaf(Bx, Ay, -By * Ax);
-
-    constexpr float eps = 1e-7;
-    if (U > -eps && U < eps) U = 0.f;
-    if (V > -eps && V < eps) V = 0.f;
-    if (W > -eps && W < eps) W = 0.f;
-
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-
-    if (U == 0.0f || V == 0.0f || W == 0.0f) {
-        // edge case: redo the edge functions in double precision
-        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
-        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
-        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
-        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    }
-
-    const float det = U + V + W;
-    if (det == 0.f) return false;
-
-    const float Az = rs.Sz * a_kz, Bz = rs.Sz * b_kz, Cz = rs.Sz * c_kz;
-    const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
-
-    const u32 sign = __float_as_uint(det) & 0x80000000u;
-    const float xor_T = __uint_as_float(__float_as_uint(T) ^ sign);
-    const float abs_det = copysignf(det, 1.f);
-    if (xor_T < 0.0f || xor_T > t_max * abs_det) return false;
-
-    const float rcp = 1.0f / det;
-    *out_t = T * rcp;
-    *out_n = madrona::math::normalize(cross(B - A, C - A));
-    return true;
+    const float inv_kz = pick(kz, inv_d.d0, inv_d.d1, inv_d.d2);
+    return RayShear { kx, ky, kz, pick(kx, d.x, d.y, d.z) * inv_kz, pick(ky, d.x, d.y, d.z) * inv_kz, inv_kz };
 }
 
 // ---- render-prepare: per-world TLAS ----------------------------------------------------------
@@ -558,27 +512,201 @@ renderBuildTLASKernel(EngineState *Sp)
 }
 
 // ---- ray casting ------------------------------------------------------------------------------
+// Closest hit of camera rays against one world.  Two ways to find the instances a ray enters:
+//   * worlds with <= kFlatInstances instances (the simulators' case: Escape Room 33): the view's
+//     block stages every instance ONCE in shared memory -- world -> object matrix, object-space
+//     camera origin, world box -- sorted front to back; each warp culls that list against the
+//     sub-frustum of its 8 x 4 pixel tile (one 64-bit mask), and a ray only slab-tests the
+//     survivors.  No tree, no per-ray quaternion algebra, a uniform loop across the warp.
+//   * larger worlds: stack traversal of the per-world TLAS (quantised 4-wide nodes).
+// Inside an instance both run the same BLAS traversal (reference-format quantised MeshBVH,
+// watertight triangle test).  Object-space rays keep the world ray's parametrisation (the
+// direction is NOT renormalised), so t needs no rescaling.
 
 struct RayHit {
     float t;
-    Vector3 normalObj;      // object-space geometric normal of the hit triangle
     int instance;           // gather index inside the world, -1: miss
     int triangle;           // triangle index inside the instance's mesh
 };
 
-// child boxes of a quantised node against the ray (mesh_bvh.inl:100-160): the slab
-// planes are evaluated straight in the node's quantised frame
+constexpr int kTraceStack = 48;     // TLAS + BLAS entries of one ray
+constexpr int kFlatInstances = 64;
+
+__device__ __forceinline__ float safeRcp(float x)
+{
+    // 1 / x; a zero component behaves like +-1e-7 (mesh_bvh.inl:100-110)
+    return x == 0.f ? copysignf(1e7f, x) : __frcp_rn(x);
+}
+
+// byte i of a packed 4 x u8 word as a float without an int -> float conversion:
+// 0x4B0000qq is the float 2^23 + qq
+template <int I>
+__device__ __forceinline__ float byteAsFloat(u32 word)
+{
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + I)) - 8388608.f;
+}
+
+// world -> object map of an instance: x_obj = m * (x_world - pos), m = scale^-1 * R(q)^T;
+// R(q) is the matrix of Quat::rotateVec (valid for slightly non-unit q as well)
+struct InstanceXform {
+    float m[9];
+};
+
+__device__ __forceinline__ InstanceXform instanceXform(const RenderInstance &inst)
+{
+    const float w = inst.rotation.w, x = inst.rotation.x, y = inst.rotation.y, z = inst.rotation.z;
+    const float diag = 1.f - 2.f * (x * x + y * y + z * z);
+    // R = diag * I + 2 u u^T + 2 w [u]x
+    const float r00 = diag + 2.f * x * x, r01 = 2.f * (x * y - w * z), r02 = 2.f * (x * z + w * y);
+    const float r10 = 2.f * (x * y + w * z), r11 = diag + 2.f * y * y, r12 = 2.f * (y * z - w * x);
+    const float r20 = 2.f * (x * z - w * y), r21 = 2.f * (y * z + w * x), r22 = diag + 2.f * z * z;
+    const float isx = __frcp_rn(inst.scale.x), isy = __frcp_rn(inst.scale.y), isz = __frcp_rn(inst.scale.z);
+    InstanceXform X;
+    X.m[0] = r00 * isx; X.m[1] = r10 * isx; X.m[2] = r20 * isx;
+    X.m[3] = r01 * isy; X.m[4] = r11 * isy; X.m[5] = r21 * isy;
+    X.m[6] = r02 * isz; X.m[7] = r12 * isz; X.m[8] = r22 * isz;
+    return X;
+}
+
+__device__ __forceinline__ Vector3 applyLinear(const float *m, Vector3 v)
+{
+    return Vector3 { m[0] * v.x + m[1] * v.y + m[2] * v.z,
+                     m[3] * v.x + m[4] * v.y + m[5] * v.z,
+                     m[6] * v.x + m[7] * v.y + m[8] * v.z };
+}
+
+__device__ __forceinline__ bool instanceTraceable(const RenderState &R, const RenderInstance &inst)
+{
+    return inst.scale.x != 0.f && inst.scale.y != 0.f && inst.scale.z != 0.f && inst.objectID >= 0 &&
+        (u32)inst.objectID < R.numMeshes;
+}
+
+// watertight ray-triangle test (Woop et al. 2013), t only
+__device__ __forceinline__ bool rayTriangleT(const BVHVertex *v, const RayShear &rs, Vector3 org, float t_min,
+                                             float t_max, float *out_t)
+{
+    const Vector3 A { v[0].pos[0] - org.x, v[0].pos[1] - org.y, v[0].pos[2] - org.z };
+    const Vector3 B { v[1].pos[0] - org.x, v[1].pos[1] - org.y, v[1].pos[2] - org.z };
+    const Vector3 C { v[2].pos[0] - org.x, v[2].pos[1] - org.y, v[2].pos[2] - org.z };
+    // component selection by compares (a dynamically indexed Vector3 would live in local memory)
+    auto pick = [](int k, const Vector3 &p) { return k == 0 ? p.x : (k == 1 ? p.y : p.z); };
+    const float a_kz = pick(rs.kz, A), a_kx = pick(rs.kx, A), a_ky = pick(rs.ky, A);
+    const float b_kz = pick(rs.kz, B), b_kx = pick(rs.kx, B), b_ky = pick(rs.ky, B);
+    const float c_kz = pick(rs.kz, C), c_kx = pick(rs.kx, C), c_ky = pick(rs.ky, C);
+
+    const float Ax = fmaf(-rs.Sx, a_kz, a_kx), Ay = fmaf(-rs.Sy, a_kz, a_ky);
+    const float Bx = fmaf(-rs.Sx, b_kz, b_kx), By = fmaf(-rs.Sy, b_kz, b_ky);
+    const float Cx = fmaf(-rs.Sx, c_kz, c_kx), Cy = fmaf(-rs.Sy, c_kz, c_ky);
+
+    float U = fmaf(Cx, By, -Cy * Bx);
+    float V = fmaf(Ax, Cy, -Ay * Cx);
+    float W = fmaf(Bx, Ay, -By * Ax);
+
+    constexpr float eps = 1e-7;
+    if (U > -eps && U < eps) U = 0.f;
+    if (V > -eps && V < eps) V = 0.f;
+    if (W > -eps && W < eps) W = 0.f;
+
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        // edge case: redo the edge functions in double precision
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    }
+
+    const float det = U + V + W;
+    if (det == 0.f) return false;
+
+    const float Az = rs.Sz * a_kz, Bz = rs.Sz * b_kz, Cz = rs.Sz * c_kz;
+    const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
+
+    const u32 sign = __float_as_uint(det) & 0x80000000u;
+    const float xor_T = __uint_as_float(__float_as_uint(T) ^ sign);
+    const float abs_det = fabsf(det);
+    if (xor_T < 0.0f || xor_T > t_max * abs_det) return false;
+
+    const float t = T * __frcp_rn(det);
+    if (!(t >= t_min)) return false;
+    *out_t = t;
+    return true;
+}
+
+// BLAS traversal of one mesh with an object-space ray; shrinks t_best, reports the triangle.
+// `stack` entries [sp0, kTraceStack) are free.
+template <bool ANY_HIT>
+__device__ __forceinline__ bool traceMesh(const MeshBVH &mesh, const Vector3 oo, const Vector3 od,
+                                          const float t_min, float &t_best, int &tri_best, int *stack,
+                                          const int sp0)
+{
+    const float ix = safeRcp(od.x), iy = safeRcp(od.y), iz = safeRcp(od.z);
+    const RayShear rs = rayShear(od, Diag3x3 { ix, iy, iz });
+    const QBVHNode *nodes = mesh.nodes;
+    const BVHVertex *verts = mesh.vertices;
+    bool hit = false;
+    int sp = sp0;
+    if (sp < kTraceStack) stack[sp++] = 0;
+    while (sp > sp0) {
+        const QBVHNode &bn = nodes[stack[--sp]];
+        // child boxes in the node's quantised frame (mesh_bvh.inl:100-160)
+        const u32 exps = *(const u32 *)&bn.expX;
+        const float sx = __uint_as_float((u32)((int)(signed char)(exps & 0xffu) + 127) << 23) * ix;
+        const float sy = __uint_as_float((u32)((int)(signed char)((exps >> 8) & 0xffu) + 127) << 23) * iy;
+        const float sz = __uint_as_float((u32)((int)(signed char)((exps >> 16) & 0xffu) + 127) << 23) * iz;
+        const float bx = (bn.minPoint[0] - oo.x) * ix;
+        const float by = (bn.minPoint[1] - oo.y) * iy;
+        const float bz = (bn.minPoint[2] - oo.z) * iz;
+        const u32 qnx = *(const u32 *)bn.qMinX, qny = *(const u32 *)bn.qMinY, qnz = *(const u32 *)bn.qMinZ;
+        const u32 qfx = *(const u32 *)bn.qMaxX, qfy = *(const u32 *)bn.qMaxY, qfz = *(const u32 *)bn.qMaxZ;
+        const u32 tri_sizes = *(const u32 *)bn.triSize;
+
+        auto visit = [&](const u32 child, const float nx, const float fx, const float ny, const float fy,
+                         const float nz, const float fz, const u32 tri_count) {
+            if (child == 0xFFFFFFFFu) return;
+            const float t_near = fmaxf(fminf(nx, fx), fmaxf(fminf(ny, fy), fmaxf(fminf(nz, fz), 0.f)));
+            const float t_far = fminf(fmaxf(nx, fx), fminf(fmaxf(ny, fy), fminf(fmaxf(nz, fz), t_best)));
+            if (!(t_near <= t_far)) return;
+            if (!(child & 0x80000000u)) {
+                if (sp < kTraceStack) stack[sp++] = (int)child;
+                return;
+            }
+            const u32 first_tri = child & 0x7FFFFFFFu;
+            for (u32 k = 0; k < tri_count; k++) {
+                float t;
+                if (rayTriangleT(verts + (size_t)(first_tri + k) * 3, rs, oo, t_min, t_best, &t)) {
+                    t_best = t;
+                    tri_best = (int)(first_tri + k);
+                    hit = true;
+                }
+            }
+        };
+        visit(bn.childrenIdx[0], byteAsFloat<0>(qnx) * sx + bx, byteAsFloat<0>(qfx) * sx + bx,
+              byteAsFloat<0>(qny) * sy + by, byteAsFloat<0>(qfy) * sy + by,
+              byteAsFloat<0>(qnz) * sz + bz, byteAsFloat<0>(qfz) * sz + bz, tri_sizes & 0xffu);
+        visit(bn.childrenIdx[1], byteAsFloat<1>(qnx) * sx + bx, byteAsFloat<1>(qfx) * sx + bx,
+              byteAsFloat<1>(qny) * sy + by, byteAsFloat<1>(qfy) * sy + by,
+              byteAsFloat<1>(qnz) * sz + bz, byteAsFloat<1>(qfz) * sz + bz, (tri_sizes >> 8) & 0xffu);
+        visit(bn.childrenIdx[2], byteAsFloat<2>(qnx) * sx + bx, byteAsFloat<2>(qfx) * sx + bx,
+              byteAsFloat<2>(qny) * sy + by, byteAsFloat<2>(qfy) * sy + by,
+              byteAsFloat<2>(qnz) * sz + bz, byteAsFloat<2>(qfz) * sz + bz, (tri_sizes >> 16) & 0xffu);
+        visit(bn.childrenIdx[3], byteAsFloat<3>(qnx) * sx + bx, byteAsFloat<3>(qfx) * sx + bx,
+              byteAsFloat<3>(qny) * sy + by, byteAsFloat<3>(qfy) * sy + by,
+              byteAsFloat<3>(qnz) * sz + bz, byteAsFloat<3>(qfz) * sz + bz, (tri_sizes >> 24) & 0xffu);
+        if (ANY_HIT && hit) return true;
+    }
+    return hit;
+}
+
+// child boxes of a quantised TLAS node against a world-space ray
 struct NodeRay {
     float dirX, dirY, dirZ;     // 2^exp / d
     float orgX, orgY, orgZ;     // (minPoint - o) / d
 };
 
-__device__ __forceinline__ NodeRay nodeRay(const QBVHNode &node, Vector3 o, Vector3 d)
+__device__ __forceinline__ NodeRay nodeRay(const QBVHNode &node, Vector3 o, float ix, float iy, float iz)
 {
-    constexpr float diveps = 0.0000001f;
-    const float ix = copysignf(d.x == 0 ? 1 / diveps : 1 / d.x, d.x);
-    const float iy = copysignf(d.y == 0 ? 1 / diveps : 1 / d.y, d.y);
-    const float iz = copysignf(d.z == 0 ? 1 / diveps : 1 / d.z, d.z);
     NodeRay r;
     r.dirX = __uint_as_float((u32)(node.expX + 127) << 23) * ix;
     r.dirY = __uint_as_float((u32)(node.expY + 127) << 23) * iy;
@@ -599,21 +727,20 @@ __device__ __forceinline__ bool childHit(const QBVHNode &node, const NodeRay &r,
     return t_near <= t_far;
 }
 
-constexpr int kTraceStack = 48;
-
-// Closest hit (ANY_HIT: first hit) of a world-space ray against one world.
+// Closest hit (ANY_HIT: first hit) of a world-space ray through the world's TLAS.
 template <bool ANY_HIT>
 __device__ RayHit traceWorld(const RenderState &R, const QBVHNode *tlas, const i32 tlas_nodes,
                              const RenderInstance *instances, Vector3 o, Vector3 d, float t_min, float t_max,
                              int *stack)
 {
-    RayHit hit { t_max, Vector3 { 0, 0, 0 }, -1, -1 };
+    RayHit hit { t_max, -1, -1 };
     if (tlas_nodes <= 0) return hit;
+    const float ix = safeRcp(d.x), iy = safeRcp(d.y), iz = safeRcp(d.z);
     int sp = 0;
     stack[sp++] = 0;
     while (sp > 0) {
         const QBVHNode &node = tlas[stack[--sp]];
-        const NodeRay nr = nodeRay(node, o, d);
+        const NodeRay nr = nodeRay(node, o, ix, iy, iz);
 #pragma unroll
         for (int c = 0; c < kBVHWidth; c++) {
             const u32 child = node.childrenIdx[c];
@@ -623,71 +750,76 @@ __device__ RayHit traceWorld(const RenderState &R, const QBVHNode *tlas, const i
                 if (sp < kTraceStack) stack[sp++] = (int)child;
                 continue;
             }
-            // ---- an instance: object-space ray; t is rescaled by |d'| while inside the mesh
             const int ii = (int)(child & 0x7FFFFFFFu);
             const RenderInstance &inst = instances[ii];
-            if (inst.scale.x == 0.f || inst.scale.y == 0.f || inst.scale.z == 0.f || inst.objectID < 0 ||
-                    (u32)inst.objectID >= R.numMeshes) {
-                continue;
-            }
-            const MeshBVH &mesh = R.meshes[inst.objectID];
-            const Quat q { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
-            const Diag3x3 inv_scale = Diag3x3 { inst.scale.x, inst.scale.y, inst.scale.z }.inv();
-            const Vector3 p { inst.position.x, inst.position.y, inst.position.z };
-            const Vector3 oo = inv_scale * q.inv().rotateVec(o - p);
-            Vector3 od = inv_scale * q.inv().rotateVec(d);
-            const float t_scale = od.length();
-            od /= t_scale;
-            float t_obj = hit.t * t_scale;
-            const float t_obj_min = t_min * t_scale;
-            const Diag3x3 inv_od = Diag3x3::fromVec(od).inv();
-            const RayShear rs = rayShear(od, inv_od);
-
-            bool hit_here = false;
-            Vector3 n_obj { 0, 0, 0 };
-            int tri_here = -1;
-            const int blas_base = sp;
-            if (sp < kTraceStack) stack[sp++] = 0;
-            while (sp > blas_base) {
-                const QBVHNode &bn = mesh.nodes[stack[--sp]];
-                const NodeRay br = nodeRay(bn, oo, od);
-#pragma unroll
-                for (int bc = 0; bc < kBVHWidth; bc++) {
-                    const u32 bchild = bn.childrenIdx[bc];
-                    if (bchild == 0xFFFFFFFFu) continue;
-                    if (!childHit(bn, br, bc, t_obj)) continue;
-                    if (!(bchild & 0x80000000u)) {
-                        if (sp < kTraceStack) stack[sp++] = (int)bchild;
-                        continue;
-                    }
-                    const u32 first_tri = bchild & 0x7FFFFFFFu;
-                    for (u32 k = 0; k < bn.triSize[bc]; k++) {
-                        const BVHVertex *v = mesh.vertices + (size_t)(first_tri + k) * 3;
-                        const Vector3 a { v[0].pos[0], v[0].pos[1], v[0].pos[2] };
-                        const Vector3 b { v[1].pos[0], v[1].pos[1], v[1].pos[2] };
-                        const Vector3 cc { v[2].pos[0], v[2].pos[1], v[2].pos[2] };
-                        float t;
-                        Vector3 nn;
-                        if (rayTriangle(a, b, cc, rs, oo, t_obj, &t, &nn) && t >= t_obj_min) {
-                            t_obj = t;
-                            hit_here = true;
-                            n_obj = nn;
-                            tri_here = (int)(first_tri + k);
-                        }
-                    }
-                }
-                if (ANY_HIT && hit_here) {
-                    sp = blas_base;
-                    break;
-                }
-            }
-            if (hit_here) {
-                hit.t = t_obj / t_scale;
-                hit.normalObj = n_obj;
+            if (!instanceTraceable(R, inst)) continue;
+            const InstanceXform X = instanceXform(inst);
+            const Vector3 oo = applyLinear(X.m, o - Vector3 { inst.position.x, inst.position.y, inst.position.z });
+            const Vector3 od = applyLinear(X.m, d);
+            int tri = -1;
+            if (traceMesh<ANY_HIT>(R.meshes[inst.objectID], oo, od, t_min, hit.t, tri, stack, sp)) {
                 hit.instance = ii;
-                hit.triangle = tri_here;
+                hit.triangle = tri;
                 if (ANY_HIT) return hit;
             }
+        }
+    }
+    return hit;
+}
+
+// One instance staged for a view (shared memory)
+struct FlatInstance {
+    float m[9];             // world -> object, linear part
+    float pos[3];           // instance position
+    float oo[3];            // object-space origin of the view's primary rays
+    float lo[3], hi[3];     // world box relative to the view origin
+    i32 index;              // gather index inside the world (RayHit::instance)
+    i32 mesh;               // MeshBVH index; -1: nothing to trace (bad scale / object id)
+    i32 inView;             // reaches into the view frustum (camera rays only need these)
+};
+
+// world box (relative to o) against a ray from o: entered before t_max?
+__device__ __forceinline__ bool boxHit(const float *lo, const float *hi, float ix, float iy, float iz, float t_max)
+{
+    const float nx = lo[0] * ix, fx = hi[0] * ix;
+    const float ny = lo[1] * iy, fy = hi[1] * iy;
+    const float nz = lo[2] * iz, fz = hi[2] * iz;
+    const float t_near = fmaxf(fminf(nx, fx), fmaxf(fminf(ny, fy), fmaxf(fminf(nz, fz), 0.f)));
+    const float t_far = fminf(fmaxf(nx, fx), fminf(fmaxf(ny, fy), fminf(fmaxf(nz, fz), t_max)));
+    return t_near <= t_far;
+}
+
+// Closest / first hit against the staged instance list.  PRIMARY: the ray starts at the view
+// origin (staged object-space origin and relative boxes are used as they are); otherwise
+// `shift` = view origin - ray origin re-bases them.
+template <bool ANY_HIT, bool PRIMARY>
+__device__ __forceinline__ RayHit traceFlat(const RenderState &R, const FlatInstance *list, unsigned long long mask,
+                                            Vector3 o, Vector3 d, Vector3 shift, float t_min, float t_max,
+                                            int *stack)
+{
+    RayHit hit { t_max, -1, -1 };
+    const float ix = safeRcp(d.x), iy = safeRcp(d.y), iz = safeRcp(d.z);
+    while (mask) {
+        const int k = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const FlatInstance &fi = list[k];
+        bool enter;
+        if (PRIMARY) {
+            enter = boxHit(fi.lo, fi.hi, ix, iy, iz, hit.t);
+        } else {
+            const float lo[3] = { fi.lo[0] + shift.x, fi.lo[1] + shift.y, fi.lo[2] + shift.z };
+            const float hi[3] = { fi.hi[0] + shift.x, fi.hi[1] + shift.y, fi.hi[2] + shift.z };
+            enter = boxHit(lo, hi, ix, iy, iz, hit.t);
+        }
+        if (!enter) continue;
+        const Vector3 oo = PRIMARY ? Vector3 { fi.oo[0], fi.oo[1], fi.oo[2] }
+                                   : applyLinear(fi.m, o - Vector3 { fi.pos[0], fi.pos[1], fi.pos[2] });
+        const Vector3 od = applyLinear(fi.m, d);
+        int tri = -1;
+        if (traceMesh<ANY_HIT>(R.meshes[fi.mesh], oo, od, t_min, hit.t, tri, stack, 0)) {
+            hit.instance = fi.index;
+            hit.triangle = tri;
+            if (ANY_HIT) return hit;
         }
     }
     return hit;
@@ -698,7 +830,22 @@ __device__ __forceinline__ Vector3 hexToRgb(u32 hex)
     return Vector3 { ((hex >> 16) & 0xFF) / 255.0f, ((hex >> 8) & 0xFF) / 255.0f, (hex & 0xFF) / 255.0f };
 }
 
-__global__ void __launch_bounds__(256, 3)
+// is the box (lo, hi relative to the apex) completely on the negative side of the plane n . x = 0 ?
+__device__ __forceinline__ bool boxOutside(const float *lo, const float *hi, Vector3 n)
+{
+    const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+    const float hx = 0.5f * (hi[0] - lo[0]), hy = 0.5f * (hi[1] - lo[1]), hz = 0.5f * (hi[2] - lo[2]);
+    const float reach = n.x * cx + n.y * cy + n.z * cz + fabsf(n.x) * hx + fabsf(n.y) * hy + fabsf(n.z) * hz;
+    return reach < 0.f;
+}
+
+#ifndef MB2_RAYCAST_MINB
+#define MB2_RAYCAST_MINB 3
+#endif
+// FLAT: this launch traces the views of worlds with <= kFlatInstances instances, the other
+// instantiation the rest (a view belongs to exactly one of the two launches)
+template <bool FLAT>
+__global__ void __launch_bounds__(256, MB2_RAYCAST_MINB)
 renderRaycastKernel(EngineState *Sp)
 {
     pdlSync();
@@ -708,11 +855,16 @@ renderRaycastKernel(EngineState *Sp)
     const i32 num_views = min(out_tbl.numRows, R.maxViews);
     const u32 res = R.resolution;
     // One block traces a whole view; a warp traces 8 x 4 pixel tiles: coherent
-    // rays (same nodes entered, same dominant axis) instead of 32-pixel row segments.
+    // rays (same instances entered, same dominant axis) instead of 32-pixel row segments.
     const u32 tiles_x = (res + 7) / 8;
     const u32 num_tiles = tiles_x * ((res + 3) / 4);
     const size_t bytes_per_view = (size_t)res * res * 4;
+    const int lane = threadIdx.x & 31;
     int stack[kTraceStack];
+
+    __shared__ FlatInstance s_list[kFlatInstances];      // sorted front to back
+    __shared__ FlatInstance s_unsorted[kFlatInstances];
+    __shared__ float s_key[kFlatInstances];
 
     for (i32 v = blockIdx.y; v < num_views; v += gridDim.y) {
         const RenderView view = R.views[v];
@@ -720,8 +872,11 @@ renderRaycastKernel(EngineState *Sp)
         const QBVHNode *tlas = R.tlasNodes + (size_t)w * R.maxInstancesPerWorld;
         const i32 tlas_nodes = R.tlasNodeCounts[w];
         const RenderInstance *instances = R.instances + (size_t)w * R.maxInstancesPerWorld;
+        const i32 num_instances = R.instanceCounts[w];
         const RenderLight *lights = R.lights + (size_t)w * kMaxLightsPerWorld;
         const i32 num_lights = R.lightCounts[w];
+        constexpr bool flat = FLAT;
+        if ((num_instances <= kFlatInstances) != FLAT) continue;
 
         // camera frame (shared by every pixel of the view)
         const Quat rot { view.rotation.w, view.rotation.x, view.rotation.y, view.rotation.z };
@@ -733,9 +888,93 @@ renderRaycastKernel(EngineState *Sp)
         const Vector3 u = rot.inv().rotateVec({ 1, 0, 0 });
         const Vector3 vv = cross(forward, u).normalize();
 
+        // ---- stage the world's instances, front to back, culled against the view frustum
+        __syncthreads();        // the previous view's rays are done with the list
+        if (flat) {
+            const int i = (int)threadIdx.x;
+            if (i < num_instances) {
+                FlatInstance &fi = s_unsorted[i];
+                const RenderInstance &inst = instances[i];
+                fi.index = i;
+                fi.mesh = instanceTraceable(R, inst) ? inst.objectID : -1;
+                const InstanceXform X = instanceXform(inst);
+#pragma unroll
+                for (int k = 0; k < 9; k++) fi.m[k] = X.m[k];
+                fi.pos[0] = inst.position.x; fi.pos[1] = inst.position.y; fi.pos[2] = inst.position.z;
+                const Vector3 oo = applyLinear(X.m, ray_start - Vector3 { inst.position.x, inst.position.y,
+                                                                           inst.position.z });
+                fi.oo[0] = oo.x; fi.oo[1] = oo.y; fi.oo[2] = oo.z;
+                float lo[3], hi[3];
+                float dist2 = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    lo[a] = inst.aabbMin[a] - ray_start[a];
+                    hi[a] = inst.aabbMax[a] - ray_start[a];
+                    fi.lo[a] = lo[a];
+                    fi.hi[a] = hi[a];
+                    const float gap = fmaxf(fmaxf(lo[a], -hi[a]), 0.f);    // distance to the box on this axis
+                    dist2 += gap * gap;
+                }
+                // whole-view frustum: |a| <= h c, |b| <= h c, c >= 0 in the (u, vv, forward) frame
+                const float pad = h * (1.f + 2.f / (float)res);
+                const bool outside = boxOutside(lo, hi, forward) ||
+                    boxOutside(lo, hi, u + pad * forward) || boxOutside(lo, hi, pad * forward - u) ||
+                    boxOutside(lo, hi, vv + pad * forward) || boxOutside(lo, hi, pad * forward - vv);
+                fi.inView = outside ? 0 : 1;
+                s_key[i] = dist2;
+            }
+            __syncthreads();
+            if (i < num_instances) {
+                const float key = s_key[i];
+                int rank = 0;
+                for (int j = 0; j < num_instances; j++) {
+                    const float kj = s_key[j];
+                    rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+                }
+                const u32 *src = (const u32 *)&s_unsorted[i];
+                u32 *dst = (u32 *)&s_list[rank];
+#pragma unroll
+                for (int k = 0; k < (int)(sizeof(FlatInstance) / 4); k++) dst[k] = src[k];
+            }
+            __syncthreads();
+        }
+
+        // instances a shadow ray may hit: all with a mesh (warp-uniform mask)
+        unsigned long long mesh_mask = 0;
+        if (flat && num_lights > 0) {
+#pragma unroll
+            for (int half = 0; half < kFlatInstances / 32; half++) {
+                const int k = half * 32 + lane;
+                const bool keep = k < num_instances && s_list[k].mesh >= 0;
+                mesh_mask |= (unsigned long long)__ballot_sync(0xffffffffu, keep) << (32 * half);
+            }
+        }
+
         for (u32 tile = threadIdx.x >> 5; tile < num_tiles; tile += blockDim.x >> 5) {
-            const u32 px = (tile % tiles_x) * 8 + (threadIdx.x & 7);
-            const u32 py = (tile / tiles_x) * 4 + ((threadIdx.x & 31) >> 3);
+            const u32 tx0 = (tile % tiles_x) * 8, ty0 = (tile / tiles_x) * 4;
+            const u32 px = tx0 + (threadIdx.x & 7);
+            const u32 py = ty0 + ((threadIdx.x & 31) >> 3);
+
+            // ---- instances that reach into this tile's sub-frustum (warp-uniform mask)
+            unsigned long long tile_mask = 0;
+            if (flat) {
+                const float inv_res = 1.f / (float)res;
+                const float a0 = ((float)tx0 * inv_res - 0.5f) * viewport, a1 = ((float)(tx0 + 8) * inv_res - 0.5f) * viewport;
+                const float b0 = ((float)ty0 * inv_res - 0.5f) * viewport, b1 = ((float)(ty0 + 4) * inv_res - 0.5f) * viewport;
+                const Vector3 n_left = u - a0 * forward, n_right = a1 * forward - u;
+                const Vector3 n_bottom = vv - b0 * forward, n_top = b1 * forward - vv;
+#pragma unroll
+                for (int half = 0; half < kFlatInstances / 32; half++) {
+                    const int k = half * 32 + lane;
+                    bool keep = false;
+                    if (k < num_instances) {
+                        const FlatInstance &fi = s_list[k];
+                        keep = fi.mesh >= 0 && fi.inView && !boxOutside(fi.lo, fi.hi, n_left) && !boxOutside(fi.lo, fi.hi, n_right) &&
+                            !boxOutside(fi.lo, fi.hi, n_bottom) && !boxOutside(fi.lo, fi.hi, n_top);
+                    }
+                    tile_mask |= (unsigned long long)__ballot_sync(0xffffffffu, keep) << (32 * half);
+                }
+            }
             if (px >= res || py >= res) continue;
 
             // ---- primary ray (bvh_raycast.cpp:58-88)
@@ -747,8 +986,9 @@ renderRaycastKernel(EngineState *Sp)
             Vector3 ray_dir = lower_left + pu * horizontal + pv * vertical - ray_start;
             ray_dir = ray_dir.normalize();
 
-            const RayHit first = traceWorld<false>(R, tlas, tlas_nodes, instances, ray_start, ray_dir, 0.f,
-                                                   10000.f, stack);
+            const RayHit first = flat
+                ? traceFlat<false, true>(R, s_list, tile_mask, ray_start, ray_dir, Vector3 { 0, 0, 0 }, 0.f, 10000.f, stack)
+                : traceWorld<false>(R, tlas, tlas_nodes, instances, ray_start, ray_dir, 0.f, 10000.f, stack);
             const bool hit = first.instance >= 0;
 
             const size_t pix = (size_t)px + (size_t)py * res;
@@ -780,41 +1020,53 @@ renderRaycastKernel(EngineState *Sp)
                     const RenderMaterial &m = R.materials[material_idx];
                     base = Vector3 { m.color[0], m.color[1], m.color[2] };
                 }
-                const Quat iq { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
-                const Vector3 normal = iq.rotateVec(first.normalObj);
 
-                // lights (bvh_raycast.cpp:861-919)
-                const Vector3 hit_pos = ray_start + first.t * ray_dir;
                 float light_contrib = 0.f;
-                for (i32 li = 0; li < num_lights; li++) {
-                    const RenderLight &l = lights[li];
-                    const Vector3 ldir_in { l.direction.x, l.direction.y, l.direction.z };
-                    Vector3 light_dir = -ldir_in;
-                    if (!l.directional) {
-                        light_dir = (Vector3 { l.position.x, l.position.y, l.position.z } - hit_pos).normalize();
-                        if (l.cutoff != -1.f) {
-                            float dd = dot(-light_dir, ldir_in);
-                            dd /= (light_dir.length() * ldir_in.length());
-                            const float angle = acosf(dd);
-                            if (fabsf(angle) > fabsf(l.cutoff)) continue;
-                        }
-                    }
-                    if (l.castShadow) {
-                        if (dot(light_dir, normal) > 0.f) {
-                            // The reference starts the shadow ray AT the fp32 hit point with tMin 1e-6
-                            // (bvh_raycast.cpp:893-901): whether it re-hits its own triangle then
-                            // depends on which side of the surface the rounded point fell (measured
-                            // here: ~10 % of lit pixels flicker).  Deliberate deviation: the origin is
-                            // lifted 1 mm along the surface normal (which faces the light in this branch).
-                            const RayHit shadow = traceWorld<true>(R, tlas, tlas_nodes, instances,
-                                                                   hit_pos + 0.001f * normal, light_dir, 0.000001f,
-                                                                   10000.f, stack);
-                            if (shadow.instance < 0) {
-                                light_contrib += fminf(fmaxf(dot(normal, light_dir), 0.f), 1.f);
+                if (num_lights > 0) {
+                    // geometric normal of the hit triangle: object space, rotated by the instance
+                    // rotation (scale ignored, as the reference does)
+                    const BVHVertex *tv = mesh.vertices + (size_t)first.triangle * 3;
+                    const Vector3 ta { tv[0].pos[0], tv[0].pos[1], tv[0].pos[2] };
+                    const Vector3 tb { tv[1].pos[0], tv[1].pos[1], tv[1].pos[2] };
+                    const Vector3 tc { tv[2].pos[0], tv[2].pos[1], tv[2].pos[2] };
+                    const Quat iq { inst.rotation.w, inst.rotation.x, inst.rotation.y, inst.rotation.z };
+                    const Vector3 normal = iq.rotateVec(madrona::math::normalize(cross(tb - ta, tc - ta)));
+
+                    // lights (bvh_raycast.cpp:861-919)
+                    const Vector3 hit_pos = ray_start + first.t * ray_dir;
+                    for (i32 li = 0; li < num_lights; li++) {
+                        const RenderLight &l = lights[li];
+                        const Vector3 ldir_in { l.direction.x, l.direction.y, l.direction.z };
+                        Vector3 light_dir = -ldir_in;
+                        if (!l.directional) {
+                            light_dir = (Vector3 { l.position.x, l.position.y, l.position.z } - hit_pos).normalize();
+                            if (l.cutoff != -1.f) {
+                                float dd = dot(-light_dir, ldir_in);
+                                dd /= (light_dir.length() * ldir_in.length());
+                                const float angle = acosf(dd);
+                                if (fabsf(angle) > fabsf(l.cutoff)) continue;
                             }
                         }
-                    } else {
-                        light_contrib += fminf(fmaxf(dot(normal, light_dir), 0.f), 1.f);
+                        if (l.castShadow) {
+                            if (dot(light_dir, normal) > 0.f) {
+                                // The reference starts the shadow ray AT the fp32 hit point with tMin 1e-6
+                                // (bvh_raycast.cpp:893-901): whether it re-hits its own triangle then
+                                // depends on which side of the surface the rounded point fell (measured
+                                // here: ~10 % of lit pixels flicker).  Deliberate deviation: the origin is
+                                // lifted 1 mm along the surface normal (which faces the light in this branch).
+                                const Vector3 so = hit_pos + 0.001f * normal;
+                                const RayHit shadow = flat
+                                    ? traceFlat<true, false>(R, s_list, mesh_mask, so, light_dir, ray_start - so,
+                                                             0.000001f, 10000.f, stack)
+                                    : traceWorld<true>(R, tlas, tlas_nodes, instances, so, light_dir, 0.000001f,
+                                                       10000.f, stack);
+                                if (shadow.instance < 0) {
+                                    light_contrib += fminf(fmaxf(dot(normal, light_dir), 0.f), 1.f);
+                                }
+                            }
+                        } else {
+                            light_contrib += fminf(fmaxf(dot(normal, light_dir), 0.f), 1.f);
+                        }
                     }
                 }
                 color = fmaxf(0.2f, light_contrib) * base;
@@ -1073,7 +1325,8 @@ LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err)
         return nullptr;
     }
     const unsigned view_blocks = (unsigned)std::max(1, std::min(R.maxViews, 65535));
-    launchK(renderRaycastKernel, dim3(1, view_blocks), dim3(256), 0, ex->stream, ex->dState);
+    launchK(renderRaycastKernel<true>, dim3(1, view_blocks), dim3(256), 0, ex->stream, ex->dState);
+    launchK(renderRaycastKernel<false>, dim3(1, view_blocks), dim3(256), 0, ex->stream, ex->dState);
     launchStatusCopy(ex, ex->stream);
     cudaError_t e = cudaStreamEndCapture(ex->stream, &g->graph);
     if (e != cudaSuccess || cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) {
@@ -1082,7 +1335,7 @@ LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err)
         delete g;
         return nullptr;
     }
-    g->numKernels = 2;
+    g->numKernels = 3;
     return g;
 }
 

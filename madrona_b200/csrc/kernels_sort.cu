@@ -41,6 +41,8 @@ struct SortCtrl {
     int32_t blocksDone;
     int32_t didSort;
     int32_t copyBlocksDone;
+    int32_t moveTicket;               // rearrange work-item ticket
+    int32_t colDone[kMaxColumns];     // gather chunks finished per column (copy-back items wait on it)
 };
 
 struct SortScratch {
@@ -71,6 +73,8 @@ struct SortParams {
     void **alt;       // this archetype's row of altColumns
     int32_t maxTiles;
     int32_t hasExported;
+    int32_t fuseCopyBack;             // exported columns are copied back inside the rearrange kernel
+    unsigned long long exportedMask;
 };
 
 // ---- TMA (bulk async copy) staging of contiguous tiles: global -> shared memory by the
@@ -169,8 +173,12 @@ sortHistogramKernel(SortParams p)
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagInclusive = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
+#ifndef MB2_SORT_LOOK_WINDOW
+#define MB2_SORT_LOOK_WINDOW 8
+#endif
+constexpr int kLookWindow = MB2_SORT_LOOK_WINDOW;
 
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 4)
 sortOnesweepKernel(SortParams p, int pass)
 {
     pdlSync();
@@ -315,13 +323,35 @@ sortOnesweepKernel(SortParams p, int pass)
         } else {
             lb[(size_t)tile * kTileStride + d] = kFlagAggregate | tile_count;
             __threadfence();
+            // windowed look-back: kLookWindow predecessors are fetched with independent loads and
+            // consumed in order, so the serial chain of L2 round trips is 1/kLookWindow as long
+            // (with every block starting at once, tile k otherwise walks ~k/2 predecessors one
+            // dependent load at a time)
             int32_t look = tile - 1;
-            while (true) {
-                uint32_t v = lb[(size_t)look * kTileStride + d];
-                if ((v >> 30) == 0) continue;     // predecessor not published yet
-                excl += v & kValueMask;
-                if ((v >> 30) == 2u) break;
-                look--;
+            bool done = false;
+            while (!done) {
+                uint32_t v[kLookWindow];
+#pragma unroll
+                for (int j = 0; j < kLookWindow; j++) {
+                    const int32_t tl = look - j;
+                    v[j] = tl >= 0 ? lb[(size_t)tl * kTileStride + d] : 0u;
+                }
+                bool stop = false;
+                int consumed = 0;
+#pragma unroll
+                for (int j = 0; j < kLookWindow; j++) {
+                    const uint32_t flag = v[j] >> 30;
+                    if (!stop) {
+                        if (flag == 0) {
+                            stop = true;                 // predecessor not published yet: retry from it
+                        } else {
+                            excl += v[j] & kValueMask;
+                            consumed++;
+                            if (flag == 2u) { done = true; stop = true; }
+                        }
+                    }
+                }
+                look -= consumed;
             }
             lb[(size_t)tile * kTileStride + d] = kFlagInclusive | (excl + tile_count);
         }
@@ -368,32 +398,53 @@ sortOnesweepKernel(SortParams p, int pass)
 }
 
 // ---- kernel P+2: fused multi-column permutation ------------------------------------
-// A block owns tiles of kRearrangeTile consecutive OUTPUT rows: the tile's slice
-// of the permutation is staged in shared memory once and reused for every
-// column, each column is moved in its widest aligned unit (16/8/4/1 bytes) with
-// coalesced stores (source rows are mostly in order, so the gathers coalesce
-// too).  The same pass re-points entity slots, derives worldOffsets/worldCounts
-// from the sorted keys and wipes the look-back scratch; the last block flips
-// the column pointers and publishes the new row count.
+// Work items = (column, chunk of kRearrangeTile consecutive OUTPUT rows), handed out through
+// one ticket counter in COLUMN-MAJOR order: at any moment all blocks gather from the same
+// column, so the randomly accessed source column (N x 4..16 bytes) stays L2 resident and
+// every 32-byte sector is fetched from DRAM once, not once per element.  The chunk's slice
+// of the permutation is staged in shared memory by one TMA bulk copy; each column is moved
+// in its widest aligned unit (16/8/4/1 bytes) with coalesced stores, four independent
+// gathers in flight per thread.
+//
+// Exported columns must keep their address.  With fuseCopyBack their copy-back items
+// (twin -> exported address, 16-byte units) follow the column's gather items in ticket
+// order and wait on the column's chunk counter, so the twin is re-read while it is still
+// in L2 and no extra launch is needed.  Deadlock free for any grid size: a copy-back item
+// waits only for gather items with smaller tickets, which are held by running blocks and
+// never wait themselves.
+//
+// The same kernel re-points entity slots, derives worldOffsets/worldCounts from the sorted
+// keys and wipes the look-back scratch; the last block flips the column pointers and
+// publishes the new row count.
 constexpr int kRearrangeTile = 2048;
 
 template <typename UnitT>
 __device__ __forceinline__ void gatherTile(const void *src_v, void *dst_v, const int32_t *perm_s,
                                            int32_t tile_row0, int32_t rows, uint32_t units_per_row)
 {
-    const UnitT *src = (const UnitT *)src_v;
-    UnitT *dst = (UnitT *)dst_v + (size_t)tile_row0 * units_per_row;
+    const UnitT *__restrict__ src = (const UnitT *)src_v;
+    UnitT *__restrict__ dst = (UnitT *)dst_v + (size_t)tile_row0 * units_per_row;
     const uint32_t total = (uint32_t)rows * units_per_row;
+    const uint32_t B = blockDim.x;
+    uint32_t i = threadIdx.x;
     if (units_per_row == 1) {
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = src[perm_s[i]];
+        for (; i + 3 * B < total; i += 4 * B) {
+            const UnitT a = src[perm_s[i]], b = src[perm_s[i + B]];
+            const UnitT c = src[perm_s[i + 2 * B]], d = src[perm_s[i + 3 * B]];
+            dst[i] = a; dst[i + B] = b; dst[i + 2 * B] = c; dst[i + 3 * B] = d;
+        }
+        for (; i < total; i += B) dst[i] = src[perm_s[i]];
     } else if ((units_per_row & (units_per_row - 1)) == 0) {
         const int sh = __ffs(units_per_row) - 1;
         const uint32_t mask = units_per_row - 1;
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            dst[i] = src[((size_t)perm_s[i >> sh] << sh) + (i & mask)];
+        auto at = [&](uint32_t k) { return src[((size_t)perm_s[k >> sh] << sh) + (k & mask)]; };
+        for (; i + 3 * B < total; i += 4 * B) {
+            const UnitT a = at(i), b = at(i + B), c = at(i + 2 * B), d = at(i + 3 * B);
+            dst[i] = a; dst[i + B] = b; dst[i + 2 * B] = c; dst[i + 3 * B] = d;
         }
+        for (; i < total; i += B) dst[i] = at(i);
     } else {
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        for (; i < total; i += B) {
             const uint32_t r = i / units_per_row;
             dst[i] = src[(size_t)perm_s[r] * units_per_row + (i - r * units_per_row)];
         }
@@ -411,82 +462,135 @@ sortRearrangeKernel(SortParams p)
     const int last = (p.numPasses - 1) & 1;
     const int32_t *perm = p.idx[last];
     const uint32_t *sorted_keys = p.keys[last];
+    const int32_t num_cols = t.numColumns;
+    const unsigned long long fused_mask = p.fuseCopyBack ? p.exportedMask : 0ull;
 
     __shared__ __align__(128) int32_t perm_s[kRearrangeTile];
     __shared__ __align__(8) unsigned long long perm_bar;
+    __shared__ int32_t item_s;
     if (threadIdx.x == 0) mbarInit(&perm_bar, 1);
     uint32_t perm_phase = 0;
 
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     // scratch of the finished radix passes: wiped here, spread over all blocks
     {
         const int64_t tiles = (n + kTileItems - 1) / kTileItems;
-        const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
         for (int64_t i = gtid; i < tiles * kMaxPasses * 256; i += gstride) p.lookback[i] = 0;
         for (int64_t i = gtid; i < p.numPasses * 256; i += gstride) p.bins[i] = 0;
     }
+    // world boundaries from the sorted keys
+    if (p.worldSort) {
+        for (int64_t r64 = gtid; r64 < new_n; r64 += gstride) {
+            const int32_t r = (int32_t)r64;
+            const uint32_t k = sorted_keys[r];
+            if (r == 0 || sorted_keys[r - 1] != k) {
+                int32_t end = r + 1;
+                while (end < new_n && sorted_keys[end] == k) end++;
+                t.worldOffsets[k] = r;
+                t.worldCounts[k] = end - r;
+            }
+        }
+    }
 
-    const int32_t num_tiles = (new_n + kRearrangeTile - 1) / kRearrangeTile;
-    for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int32_t row0 = tile * kRearrangeTile;
-        const int32_t rows = min(kRearrangeTile, new_n - row0);
+    // ---- column moves: ticketed (phase, chunk) items; phases = G(col 0) [C(col 0)] G(col 1) ...
+    const int32_t chunks = (new_n + kRearrangeTile - 1) / kRearrangeTile;
+    const int32_t num_phases = num_cols + __popcll(fused_mask & ((num_cols >= 64) ? ~0ull : ((1ull << num_cols) - 1ull)));
+    const int64_t num_items = (int64_t)chunks * num_phases;
+    int32_t staged_chunk = -1;      // which slice of the permutation perm_s holds
+    while (true) {
+        __syncthreads();            // the previous item is done with perm_s / item_s
+        if (threadIdx.x == 0) item_s = atomicAdd(&p.ctrl->moveTicket, 1);
         __syncthreads();
-        if (rows == kRearrangeTile) {
-            // the tile's slice of the permutation: one bulk copy
+        const int64_t item = item_s;
+        if (item >= num_items) break;
+        int32_t phase = (int32_t)(item / chunks);
+        const int32_t chunk = (int32_t)(item - (int64_t)phase * chunks);
+        // phase -> (column, gather | copy-back)
+        int32_t col = 0;
+        bool copy_back = false;
+        for (; col < num_cols; col++) {
+            const int32_t span = 1 + (int32_t)((fused_mask >> col) & 1ull);
+            if (phase < span) { copy_back = phase == 1; break; }
+            phase -= span;
+        }
+        const int32_t row0 = chunk * kRearrangeTile;
+        const int32_t rows = min(kRearrangeTile, new_n - row0);
+        const uint32_t bytes = t.columnBytes[col];
+
+        if (copy_back) {
+            // every gather chunk of this column has landed in the twin
             if (threadIdx.x == 0) {
-                mbarExpectTx(&perm_bar, kRearrangeTile * 4);
-                tmaLoad1D(perm_s, perm + row0, kRearrangeTile * 4, &perm_bar);
+                volatile int32_t *done = &p.ctrl->colDone[col];
+                while (*done < chunks) { }
+                __threadfence();
             }
-            mbarWait(&perm_bar, perm_phase);
-            perm_phase ^= 1u;
-        } else {
-            for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
             __syncthreads();
+            // (columns are 256-byte aligned with 256 bytes of slack: whole 16-byte units;
+            //  row0 * bytes is a multiple of 2048)
+            const uint4 *src = (const uint4 *)((const char *)p.alt[col] + (size_t)row0 * bytes);
+            uint4 *dst = (uint4 *)((char *)t.columns[col] + (size_t)row0 * bytes);
+            const uint32_t units = (uint32_t)(((size_t)rows * bytes + 15) / 16);
+            const uint32_t B = blockDim.x;
+            uint32_t i = threadIdx.x;
+            for (; i + 3 * B < units; i += 4 * B) {
+                const uint4 a = __ldcg(src + i), b = __ldcg(src + i + B);
+                const uint4 c = __ldcg(src + i + 2 * B), d = __ldcg(src + i + 3 * B);
+                dst[i] = a; dst[i + B] = b; dst[i + 2 * B] = c; dst[i + 3 * B] = d;
+            }
+            for (; i < units; i += B) dst[i] = __ldcg(src + i);
+            continue;
         }
 
-        for (int32_t col = 0; col < t.numColumns; col++) {
-            const void *src = t.columns[col];
-            void *dst = p.alt[col];
-            const uint32_t bytes = t.columnBytes[col];
-            if (col == 0) {
-                // Entity column: move + re-point the entity slot at the new row
-                // (sort_archetype.cpp:1357-1379)
-                const unsigned long long *sp = (const unsigned long long *)src;
-                unsigned long long *dp = (unsigned long long *)dst;
-                EntitySlot *slots = p.state->entitySlots;
-                for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) {
-                    const unsigned long long e = sp[perm_s[i]];
-                    dp[row0 + i] = e;
-                    const uint32_t gen = (uint32_t)(e & 0xFFFFFFFFull);
-                    const int32_t id = (int32_t)(uint32_t)(e >> 32);
-                    if (id >= 0 && gen != 0xFFFFFFFFu && id < p.state->entityCapacity &&
-                            slots[id].gen == gen && slots[id].a == (int32_t)p.archetype) {
-                        slots[id].b = row0 + i;
-                    }
+        if (staged_chunk != chunk) {
+            if (rows == kRearrangeTile) {
+                // the chunk's slice of the permutation: one bulk copy
+                if (threadIdx.x == 0) {
+                    fenceProxyAsync();
+                    mbarExpectTx(&perm_bar, kRearrangeTile * 4);
+                    tmaLoad1D(perm_s, perm + row0, kRearrangeTile * 4, &perm_bar);
                 }
-            } else if ((bytes & 15u) == 0) {
-                gatherTile<uint4>(src, dst, perm_s, row0, rows, bytes >> 4);
-            } else if ((bytes & 7u) == 0) {
-                gatherTile<uint2>(src, dst, perm_s, row0, rows, bytes >> 3);
-            } else if ((bytes & 3u) == 0) {
-                gatherTile<uint32_t>(src, dst, perm_s, row0, rows, bytes >> 2);
+                mbarWait(&perm_bar, perm_phase);
+                perm_phase ^= 1u;
             } else {
-                gatherTile<unsigned char>(src, dst, perm_s, row0, rows, bytes);
+                for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
+                __syncthreads();
             }
+            staged_chunk = chunk;
         }
 
-        // world boundaries from the sorted keys
-        if (p.worldSort) {
+        const void *src = t.columns[col];
+        void *dst = p.alt[col];
+        if (col == 0) {
+            // Entity column: move + re-point the entity slot at the new row
+            // (sort_archetype.cpp:1357-1379)
+            const unsigned long long *sp = (const unsigned long long *)src;
+            unsigned long long *dp = (unsigned long long *)dst;
+            EntitySlot *slots = p.state->entitySlots;
             for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) {
-                const int32_t r = row0 + i;
-                const uint32_t k = sorted_keys[r];
-                if (r == 0 || sorted_keys[r - 1] != k) {
-                    int32_t end = r + 1;
-                    while (end < new_n && sorted_keys[end] == k) end++;
-                    t.worldOffsets[k] = r;
-                    t.worldCounts[k] = end - r;
+                const unsigned long long e = sp[perm_s[i]];
+                dp[row0 + i] = e;
+                const uint32_t gen = (uint32_t)(e & 0xFFFFFFFFull);
+                const int32_t id = (int32_t)(uint32_t)(e >> 32);
+                if (id >= 0 && gen != 0xFFFFFFFFu && id < p.state->entityCapacity &&
+                        slots[id].gen == gen && slots[id].a == (int32_t)p.archetype) {
+                    slots[id].b = row0 + i;
                 }
             }
+        } else if ((bytes & 15u) == 0) {
+            gatherTile<uint4>(src, dst, perm_s, row0, rows, bytes >> 4);
+        } else if ((bytes & 7u) == 0) {
+            gatherTile<uint2>(src, dst, perm_s, row0, rows, bytes >> 3);
+        } else if ((bytes & 3u) == 0) {
+            gatherTile<uint32_t>(src, dst, perm_s, row0, rows, bytes >> 2);
+        } else {
+            gatherTile<unsigned char>(src, dst, perm_s, row0, rows, bytes);
+        }
+        if ((fused_mask >> col) & 1ull) {
+            // publish the chunk to the column's copy-back items
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&p.ctrl->colDone[col], 1);
         }
     }
 
@@ -502,7 +606,9 @@ sortRearrangeKernel(SortParams p)
     if (!is_last) return;
     __threadfence();
 
-    for (int c = threadIdx.x; c < t.numColumns; c += blockDim.x) {
+    for (int c = threadIdx.x; c < num_cols; c += blockDim.x) {
+        p.ctrl->colDone[c] = 0;
+        if ((fused_mask >> c) & 1ull) continue;     // already back at its exported address
         void *old_main = t.columns[c];
         t.columns[c] = p.alt[c];
         p.alt[c] = old_main;
@@ -517,7 +623,8 @@ sortRearrangeKernel(SortParams p)
         for (int i = 0; i < kMaxPasses; i++) p.ctrl->tickets[i] = 0;
         p.ctrl->numDeleted = 0;
         p.ctrl->blocksDone = 0;
-        p.ctrl->didSort = p.hasExported;
+        p.ctrl->moveTicket = 0;
+        p.ctrl->didSort = p.fuseCopyBack ? 0 : p.hasExported;
     }
 }
 
@@ -713,6 +820,12 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
         if (sc->exportedMask[archetype][c]) mask |= 1ull << c;
     }
     p.hasExported = mask ? 1 : 0;
+    p.exportedMask = mask;
+    static const int fuse_copy_back = [] {
+        const char *v = getenv("MADRONA_B200_SORT_FUSE_COPYBACK");
+        return (v && *v) ? atoi(v) : 1;
+    }();
+    p.fuseCopyBack = fuse_copy_back && mask ? 1 : 0;
 
     const int tiles = (t.capacity + kTileItems - 1) / kTileItems;
     const int hist_grid = std::max(1, std::min(tiles, ex->numSMs * 4));
@@ -728,12 +841,16 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
         launchK(sortOnesweepKernel, dim3(sweep_grid), dim3(kSortThreads), 0, s, p, pass);
     }
     const int rtiles = (t.capacity + kRearrangeTile - 1) / kRearrangeTile;
-    const int rblocks = std::max(1, std::min(rtiles, ex->numSMs * 4));
+    static const int move_per_sm = [] {
+        const char *v = getenv("MADRONA_B200_REARRANGE_BLOCKS_PER_SM");
+        return (v && *v) ? std::max(1, atoi(v)) : 8;
+    }();
+    const int rblocks = std::max(1, std::min(rtiles * std::max(1, t.numColumns / 2), ex->numSMs * move_per_sm));
     launchK(sortRearrangeKernel, dim3(rblocks), dim3(256), 0, s, p);
     const int row_blocks = std::max(1, std::min((t.capacity + 255) / 256, ex->numSMs * 4));
     dim3 rgrid((unsigned)row_blocks, (unsigned)t.numColumns);
 
-    if (mask) launchK(sortCopyBackKernel, dim3(rgrid), dim3(256), 0, s, p, mask);
+    if (mask && !p.fuseCopyBack) launchK(sortCopyBackKernel, dim3(rgrid), dim3(256), 0, s, p, mask);
 }
 
 }

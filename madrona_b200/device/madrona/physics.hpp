@@ -583,13 +583,49 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
     // then the lanes that called together run the (expensive) leaf test
     // together; the warp votes keep the compiler from folding the two phases
     // back into one divergent loop.
+    //
+    // Seed: before the ordered walk, the leaf whose slot box the ray enters FIRST is tested out
+    // of order and its hit (if any) becomes the initial t_max.  The result is unchanged: the
+    // walk's answer is "smallest hit_t, the last leaf in report order among equals" -- a leaf
+    // is accepted iff its hit_t <= t_max -- and seeding with a genuine hit only removes leaves
+    // that would lose anyway (the seed leaf itself is met again by the walk with the same
+    // t_max the unseeded walk would hold at a tie).  It matters because the report order is
+    // the tree's, not the ray's: unseeded, a lidar ray tests ~10 leaves before its nearest
+    // one shrinks t_max (ncu round 1: 11 k warp instructions per warp, 9 of 32 lanes active).
     const unsigned peers = __activemask();
     const mb2::PVec4 *boxes = s_.orderedBoxes;
     const int32_t num_boxes = s_.numTraversal;
-    int32_t k = 0;
-    bool walking = true;
     Entity closest = Entity::none();
     math::Vector3 closest_normal { 0, 0, 0 };
+    {
+        int32_t seed_leaf = -1;
+        float seed_entry = 0.f;
+        for (int32_t j = 0; j < num_boxes; j++) {
+            const mb2::PVec4 b0 = boxes[2 * j], b1 = boxes[2 * j + 1];
+            const float lx = inv_d.d0 * (b0.x - o.x), ux = inv_d.d0 * (b0.w - o.x);
+            const float ly = inv_d.d1 * (b0.y - o.y), uy = inv_d.d1 * (b1.x - o.y);
+            const float lz = inv_d.d2 * (b0.z - o.z), uz = inv_d.d2 * (b1.y - o.z);
+            const float entry = fmaxf(fminf(lx, ux), fmaxf(fminf(ly, uy), fmaxf(fminf(lz, uz), 0.f)));
+            const float exit = fminf(fmaxf(lx, ux), fminf(fmaxf(ly, uy), fminf(fmaxf(lz, uz), t_max)));
+            if (entry <= exit && (seed_leaf < 0 || entry < seed_entry)) {
+                seed_leaf = __float_as_int(b1.z);
+                seed_entry = entry;
+            }
+        }
+        __syncwarp(peers);
+        if (seed_leaf >= 0) {
+            float hit_t;
+            math::Vector3 leaf_normal;
+            if (traceRayIntoLeaf(seed_leaf, o, d, 0.f, t_max, &hit_t, &leaf_normal)) {
+                t_max = hit_t;
+                closest = unpackEntity(s_.leafEntities[seed_leaf]);
+                closest_normal = leaf_normal;
+            }
+        }
+        __syncwarp(peers);
+    }
+    int32_t k = 0;
+    bool walking = true;
 
     while (__any_sync(peers, walking)) {
         int32_t leaf_idx = -1;
