@@ -150,11 +150,40 @@ __device__ __forceinline__ T &bodyCol(const EngineState &S, const BodyArchetype 
     return ((T *)S.tables[b.archetype].columns[b.cols[pc]])[row];
 }
 
-template <typename T>
-__device__ __forceinline__ T &locCol(const EngineState &S, const PhysicsState &P, u32 arch, i32 row, int pc)
+// Column base pointers of every (rigid-body archetype, physics component), staged in shared
+// memory by each per-world / per-candidate kernel before its first access (fillColCache).
+// A component access by (archetype id, row) is then one shared-memory lookup and one global
+// load; through PhysicsState::bodyIndex -> bodies[].cols -> tables[].columns it was a chain
+// of three dependent global loads before the data (ncu, position solve: 37 % of the stall
+// samples sat on that chain).  Sorts flip column pointers only between kernels.
+struct ColCache {
+    void *ptr[kMaxBodyArchetypes][PCCount];
+    signed char bodyIndex[kMaxArchetypes];
+};
+__shared__ ColCache g_cols;
+
+__device__ __forceinline__ void fillColCache(const EngineState &S, const PhysicsState &P)
 {
-    const BodyArchetype *b = bodyOf(P, arch);
-    return ((T *)S.tables[arch].columns[b->cols[pc]])[row];
+    const int n = (int)P.numBodyArchetypes * (int)PCCount;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int bi = i / (int)PCCount, pc = i - bi * (int)PCCount;
+        const BodyArchetype &b = P.bodies[bi];
+        const i32 col = b.cols[pc];
+        g_cols.ptr[bi][pc] = col >= 0 ? S.tables[b.archetype].columns[col] : nullptr;
+    }
+    for (int i = threadIdx.x; i < kMaxArchetypes; i += blockDim.x) g_cols.bodyIndex[i] = P.bodyIndex[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool isBodyArchetype(u32 arch)
+{
+    return arch < (u32)kMaxArchetypes && g_cols.bodyIndex[arch] >= 0;
+}
+
+template <typename T>
+__device__ __forceinline__ T &locCol(const EngineState &, const PhysicsState &, u32 arch, i32 row, int pc)
+{
+    return ((T *)g_cols.ptr[g_cols.bodyIndex[arch]][pc])[row];
 }
 
 __device__ __forceinline__ WorldBVH &worldBVH(const EngineState &S, const PhysicsState &P, i32 w)
@@ -212,28 +241,19 @@ __device__ __forceinline__ void storePairs(T *p, const T &value)
     for (int i = 0; i < (int)(sizeof(T) / 8); i++) reinterpret_cast<float2 *>(p)[i] = u.v[i];
 }
 
-__device__ __forceinline__ float atomicMinFloat(float *addr, float value)
+// Float min / max as ONE native integer atomic (no CAS loop, no return value needed): for
+// value >= 0 the signed-int order of the bit patterns is the float order (every negative float
+// is a negative int), for value < 0 the unsigned order is the reversed float order.
+__device__ __forceinline__ void atomicMinFloat(float *addr, float value)
 {
-    float old = *(volatile float *)addr;
-    while (old > value) {
-        int assumed = __float_as_int(old);
-        int prev = atomicCAS((int *)addr, assumed, __float_as_int(value));
-        if (prev == assumed) break;
-        old = __int_as_float(prev);
-    }
-    return old;
+    if (value >= 0.f) atomicMin((int *)addr, __float_as_int(value));
+    else atomicMax((unsigned int *)addr, __float_as_uint(value));
 }
 
-__device__ __forceinline__ float atomicMaxFloat(float *addr, float value)
+__device__ __forceinline__ void atomicMaxFloat(float *addr, float value)
 {
-    float old = *(volatile float *)addr;
-    while (old < value) {
-        int assumed = __float_as_int(old);
-        int prev = atomicCAS((int *)addr, assumed, __float_as_int(value));
-        if (prev == assumed) break;
-        old = __int_as_float(prev);
-    }
-    return old;
+    if (value >= 0.f) atomicMax((int *)addr, __float_as_int(value));
+    else atomicMin((unsigned int *)addr, __float_as_uint(value));
 }
 
 // =============================================================================================
@@ -492,13 +512,18 @@ __device__ void refitLeaf(WorldBVH &bvh, i32 leaf)
             if (node.children[j] == child) { slot = j; break; }
         }
         if (slot < 0) return;
+        // the six bounds are fetched together (L2: other SMs grow them with atomics), the
+        // components that this leaf extends are pushed with fire-and-forget atomics; a bound
+        // that a concurrent leaf has grown past ours meanwhile only costs a redundant climb
+        const float o0 = __ldcg(&node.minX[slot]), o1 = __ldcg(&node.minY[slot]), o2 = __ldcg(&node.minZ[slot]);
+        const float o3 = __ldcg(&node.maxX[slot]), o4 = __ldcg(&node.maxY[slot]), o5 = __ldcg(&node.maxZ[slot]);
         bool grew = false;
-        grew |= box.pMin.x < atomicMinFloat(&node.minX[slot], box.pMin.x);
-        grew |= box.pMin.y < atomicMinFloat(&node.minY[slot], box.pMin.y);
-        grew |= box.pMin.z < atomicMinFloat(&node.minZ[slot], box.pMin.z);
-        grew |= box.pMax.x > atomicMaxFloat(&node.maxX[slot], box.pMax.x);
-        grew |= box.pMax.y > atomicMaxFloat(&node.maxY[slot], box.pMax.y);
-        grew |= box.pMax.z > atomicMaxFloat(&node.maxZ[slot], box.pMax.z);
+        if (box.pMin.x < o0) { atomicMinFloat(&node.minX[slot], box.pMin.x); grew = true; }
+        if (box.pMin.y < o1) { atomicMinFloat(&node.minY[slot], box.pMin.y); grew = true; }
+        if (box.pMin.z < o2) { atomicMinFloat(&node.minZ[slot], box.pMin.z); grew = true; }
+        if (box.pMax.x > o3) { atomicMaxFloat(&node.maxX[slot], box.pMax.x); grew = true; }
+        if (box.pMax.y > o4) { atomicMaxFloat(&node.maxY[slot], box.pMax.y); grew = true; }
+        if (box.pMax.z > o5) { atomicMaxFloat(&node.maxZ[slot], box.pMax.z); grew = true; }
         if (!grew) break;
         child = node_idx;
         node_idx = node.parentID;
@@ -1761,6 +1786,7 @@ physNarrowSimpleKernel(EngineState *Sp)
     pdlSync();
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
+    fillColCache(S, P);
     __shared__ i32 first[kNarrowWorldsPerBlock + 1];
     const i32 w0 = (i32)blockIdx.x * kNarrowWorldsPerBlock;
     if (threadIdx.x == 0) {
@@ -1824,6 +1850,7 @@ physNarrowHullKernel(EngineState *Sp)
     pdlSync();
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
+    fillColCache(S, P);
     __shared__ HullScratch scratch[kNarrowHullThreads / kGroupLanes];
     const int lane = threadIdx.x & 31;
     const int sub = lane % kGroupLanes;
@@ -2104,7 +2131,7 @@ __device__ void solveJoint(EngineState &S, const PhysicsState &P, const PObjectM
     if (s1.gen != j.e1Gen || s2.gen != j.e2Gen) return;
     const u32 a1 = (u32)s1.a, a2 = (u32)s2.a;
     const i32 r1row = s1.b, r2row = s2.b;
-    if (!bodyOf(P, a1) || !bodyOf(P, a2)) return;
+    if (!isBodyArchetype(a1) || !isBodyArchetype(a2)) return;
 
     Vector3 &x1_ref = locCol<Vector3>(S, P, a1, r1row, PCPosition);
     Vector3 &x2_ref = locCol<Vector3>(S, P, a2, r2row, PCPosition);
@@ -2455,6 +2482,7 @@ physWorldKernel(EngineState *Sp)
     pdlSync();
     EngineState &S = *Sp;
     const PhysicsState &P = *S.physics;
+    fillColCache(S, P);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     if constexpr (OP == PhaseSolvePositions || OP == PhaseSolveVelocities) {

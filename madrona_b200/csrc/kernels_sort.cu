@@ -583,6 +583,8 @@ sortRearrangeKernel(SortParams p)
             gatherTile<uint2>(src, dst, perm_s, row0, rows, bytes >> 3);
         } else if ((bytes & 3u) == 0) {
             gatherTile<uint32_t>(src, dst, perm_s, row0, rows, bytes >> 2);
+        } else if ((bytes & 1u) == 0) {
+            gatherTile<unsigned short>(src, dst, perm_s, row0, rows, bytes >> 1);
         } else {
             gatherTile<unsigned char>(src, dst, perm_s, row0, rows, bytes);
         }

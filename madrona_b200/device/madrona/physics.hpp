@@ -597,7 +597,10 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
     const int32_t num_boxes = s_.numTraversal;
     Entity closest = Entity::none();
     math::Vector3 closest_normal { 0, 0, 0 };
-    {
+#ifndef MB2_TRACE_SEED
+#define MB2_TRACE_SEED 1
+#endif
+    if (MB2_TRACE_SEED) {
         int32_t seed_leaf = -1;
         float seed_entry = 0.f;
         for (int32_t j = 0; j < num_boxes; j++) {
