@@ -916,7 +916,7 @@ renderRaycastKernel(EngineState *Sp)
                     dist2 += gap * gap;
                 }
                 // whole-view frustum: |a| <= h c, |b| <= h c, c >= 0 in the (u, vv, forward) frame
-                const float pad = h * (1.f + 2.f / (float)res);
+                const float pad = fabsf(h) * (1.f + 2.f / (float)res);
                 const bool outside = boxOutside(lo, hi, forward) ||
                     boxOutside(lo, hi, u + pad * forward) || boxOutside(lo, hi, pad * forward - u) ||
                     boxOutside(lo, hi, vv + pad * forward) || boxOutside(lo, hi, pad * forward - vv);
@@ -959,10 +959,15 @@ renderRaycastKernel(EngineState *Sp)
             unsigned long long tile_mask = 0;
             if (flat) {
                 const float inv_res = 1.f / (float)res;
-                const float a0 = ((float)tx0 * inv_res - 0.5f) * viewport, a1 = ((float)(tx0 + 8) * inv_res - 0.5f) * viewport;
-                const float b0 = ((float)ty0 * inv_res - 0.5f) * viewport, b1 = ((float)(ty0 + 4) * inv_res - 0.5f) * viewport;
-                const Vector3 n_left = u - a0 * forward, n_right = a1 * forward - u;
-                const Vector3 n_bottom = vv - b0 * forward, n_top = b1 * forward - vv;
+                // tile edges, a quarter pixel wider (the rays go through pixel centres)
+                const float a0 = ((float)tx0 * inv_res - 0.25f * inv_res - 0.5f) * viewport;
+                const float a1 = ((float)(tx0 + 8) * inv_res + 0.25f * inv_res - 0.5f) * viewport;
+                const float b0 = ((float)ty0 * inv_res - 0.25f * inv_res - 0.5f) * viewport;
+                const float b1 = ((float)(ty0 + 4) * inv_res + 0.25f * inv_res - 0.5f) * viewport;
+                // (a mirrored projection, h < 0, only swaps which edge is which)
+                const float al = fminf(a0, a1), ar = fmaxf(a0, a1), bl = fminf(b0, b1), br = fmaxf(b0, b1);
+                const Vector3 n_left = u - al * forward, n_right = ar * forward - u;
+                const Vector3 n_bottom = vv - bl * forward, n_top = br * forward - vv;
 #pragma unroll
                 for (int half = 0; half < kFlatInstances / 32; half++) {
                     const int k = half * 32 + lane;

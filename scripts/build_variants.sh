@@ -4,12 +4,13 @@
 # -> madrona_b200/libmadrona_b200_<name>.so (git-ignored)
 set -e
 cd "$(dirname "$0")/../madrona_b200"
+KERNEL_OBJS="build/kernels_physics.o build/kernels_sort.o build/kernels_render.o"
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
-  rm -f build/kernels_physics.o build/kernels_sort.o
+  rm -f $KERNEL_OBJS
   make -j8 NVCCFLAGS_EXTRA="$flags" > /dev/null
   cp libmadrona_b200.so libmadrona_b200_$name.so
 done
-rm -f build/kernels_physics.o build/kernels_sort.o
+rm -f $KERNEL_OBJS
 make -j8 > /dev/null
 ls -la *.so
