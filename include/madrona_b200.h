@@ -151,7 +151,12 @@ void mb2_launch_graph_destroy(mb2_launch_graph *graph);
 int mb2_run(mb2_executor *exec, mb2_launch_graph *graph);
 
 /* MWCudaExecutor::runAsync(MWCudaLaunchGraph&, cudaStream_t), mw_gpu.hpp:155
- * / cuda_exec.cpp:2796-2800: enqueue only; cuda_stream is a cudaStream_t. */
+ * / cuda_exec.cpp:2796-2800: enqueue only; cuda_stream is a cudaStream_t.
+ * The launch graphs of ONE executor share its ECS tables and the sort scratch
+ * (tickets, histograms, look-back flags): they must be ordered with respect to
+ * each other -- launch them on one stream, or chain the streams with events.
+ * Two graphs of the same executor in flight at once is undefined (the
+ * reference's megakernel has the same single-launch-at-a-time rule). */
 int mb2_run_async(mb2_executor *exec, mb2_launch_graph *graph,
                   void *cuda_stream);
 

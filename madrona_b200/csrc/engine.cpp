@@ -823,7 +823,17 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
     std::vector<cudaEvent_t> ev(order.size() + 1), ev_start(order.size());
     for (auto &e : ev) cudaEventCreate(&e);
     for (auto &e : ev_start) cudaEventCreate(&e);
+    // released on every exit path
+    struct EventGuard {
+        std::vector<cudaEvent_t> &a, &b;
+        ~EventGuard() {
+            for (auto &e : a) if (e) { cudaEventDestroy(e); e = nullptr; }
+            for (auto &e : b) if (e) { cudaEventDestroy(e); e = nullptr; }
+        }
+    } guard { ev, ev_start };
     std::vector<TableDesc> tables(S.numArchetypes);
+    // same pre-capture refresh as buildLaunchGraph (sphere narrowphase selection)
+    physicsBeforeGraphCapture(ex);
 
     for (uint32_t rep = 0; rep < reps + 1; rep++) {   // rep 0 = warm-up
         // snapshot row counts / dirty flags as they are at the start of the step
@@ -887,8 +897,6 @@ static int64_t profileNodes(Executor *ex, const uint32_t *ids, uint32_t n, uint3
             p.rows += rows;
         }
     }
-    for (auto &e : ev) cudaEventDestroy(e);
-    for (auto &e : ev_start) cudaEventDestroy(e);
 
     static const char *kind_names[] = { "parallel_for", "sort_archetype", "compact_archetype",
                                         "clear_tmp", "reset_tmp_alloc", "recycle_entities" };

@@ -2406,8 +2406,10 @@ enum PhysPhase : u32 {
     PhaseTGSVelocities, PhaseTGSPositions,
 };
 
+// (B200, room 8192 worlds, one box: 32-register build + a full wave of 8 blocks per SM
+// 1.091 ms/step, unconstrained registers + 4 blocks per SM 1.067: the default)
 #ifndef MB2_BODY_MINB
-#define MB2_BODY_MINB 8
+#define MB2_BODY_MINB 1
 #endif
 template <u32 OP>
 __global__ void __launch_bounds__(256, MB2_BODY_MINB)
@@ -2621,13 +2623,9 @@ static dim3 bodyGrid(Executor *ex)
     for (uint32_t i = 0; i < P.numBodyArchetypes; i++) {
         max_cap = std::max(max_cap, ex->hState->tables[P.bodies[i].archetype].capacity);
     }
-    // one row per thread up to a full machine of resident threads (8 blocks x 256 threads per
-    // SM): the row kernels are latency chains (row -> world -> BVH pointers -> data), so a
-    // second grid-stride iteration costs a second chain (ncu, room: 1184 blocks of 40 registers
-    // at 46 % occupancy took 37.9 us for the leaf update)
     static const int per_sm = [] {
         const char *v = getenv("MADRONA_B200_BODY_BLOCKS_PER_SM");
-        return (v && *v) ? std::max(1, atoi(v)) : 8;
+        return (v && *v) ? std::max(1, atoi(v)) : 4;
     }();
     int blocks = std::min((max_cap + 255) / 256, ex->numSMs * per_sm);
     return dim3((unsigned)std::max(blocks, 1), std::max(P.numBodyArchetypes, 1u));

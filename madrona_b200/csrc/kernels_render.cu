@@ -1329,7 +1329,10 @@ LaunchGraph *physicsBuildRenderGraph(Executor *ex, std::string *err)
         delete g;
         return nullptr;
     }
-    const unsigned view_blocks = (unsigned)std::max(1, std::min(R.maxViews, 65535));
+    // persistent blocks striding over the views (the output table's capacity can be far above
+    // the live view count: one block per capacity row cost 76 us of empty-block scheduling at
+    // 1024 worlds); 8 rounds of resident blocks keep the tail short
+    const unsigned view_blocks = (unsigned)std::max(1, std::min(R.maxViews, ex->numSMs * MB2_RAYCAST_MINB * 8));
     launchK(renderRaycastKernel<true>, dim3(1, view_blocks), dim3(256), 0, ex->stream, ex->dState);
     launchK(renderRaycastKernel<false>, dim3(1, view_blocks), dim3(256), 0, ex->stream, ex->dState);
     launchStatusCopy(ex, ex->stream);

@@ -579,56 +579,87 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
     // So the walk is a linear scan over WorldBVH::orderedBoxes -- same leaves,
     // same order, same floats, no stack and no node pointer chasing.
     //
-    // Two phases per round: every lane first scans on to its next entered leaf,
-    // then the lanes that called together run the (expensive) leaf test
-    // together; the warp votes keep the compiler from folding the two phases
-    // back into one divergent loop.
     //
-    // Seed: before the ordered walk, the leaf whose slot box the ray enters FIRST is tested out
-    // of order and its hit (if any) becomes the initial t_max.  The result is unchanged: the
-    // walk's answer is "smallest hit_t, the last leaf in report order among equals" -- a leaf
-    // is accepted iff its hit_t <= t_max -- and seeding with a genuine hit only removes leaves
-    // that would lose anyway (the seed leaf itself is met again by the walk with the same
-    // t_max the unseeded walk would hold at a tie).  It matters because the report order is
-    // the tree's, not the ray's: unseeded, a lidar ray tests ~10 leaves before its nearest
-    // one shrinks t_max (ncu round 1: 11 k warp instructions per warp, 9 of 32 lanes active).
+    // Mechanism (results identical by construction): boxes are handled in chunks of 64.
+    //   1. uniform pass: every lane slab-tests the chunk's boxes against its CURRENT t_max and
+    //      keeps the passing ones as a 64-bit mask -- all lanes run the same loop, no divergence.
+    //      t_max only shrinks afterwards and a smaller t_max can only turn a pass into a fail
+    //      (exit = min(..., t_max)), so the mask is a superset of the leaves the walk enters;
+    //   2. ordered pass over the mask bits: the slab test is REPEATED with the t_max of that
+    //      moment -- the reference's exact decision, same expression, same floats -- and the
+    //      leaves that pass are entered in order.  Each round every lane first moves on to its
+    //      next entered leaf, then the lanes that called together run the (expensive) leaf
+    //      test together; the warp votes keep the compiler from folding the two phases back
+    //      into one divergent loop.
+    // (The one-phase scan over all boxes spent most of its instructions in the divergent
+    // "walk to my next entered leaf" loop: ncu round 1, 9 of 32 lanes active.  Tried and
+    // rejected on B200, room 8192 worlds: seeding t_max with the hit of the nearest-entry leaf
+    // before the walk -- 1.091 vs 1.019 ms/step, the extra pass costs more than the leaf tests
+    // it saves.)
+#ifndef MB2_TRACE_MASK
+#define MB2_TRACE_MASK 1
+#endif
+#if MB2_TRACE_MASK
     const unsigned peers = __activemask();
     const mb2::PVec4 *boxes = s_.orderedBoxes;
     const int32_t num_boxes = s_.numTraversal;
     Entity closest = Entity::none();
     math::Vector3 closest_normal { 0, 0, 0 };
-#ifndef MB2_TRACE_SEED
-#define MB2_TRACE_SEED 1
-#endif
-    if (MB2_TRACE_SEED) {
-        int32_t seed_leaf = -1;
-        float seed_entry = 0.f;
-        for (int32_t j = 0; j < num_boxes; j++) {
-            const mb2::PVec4 b0 = boxes[2 * j], b1 = boxes[2 * j + 1];
-            const float lx = inv_d.d0 * (b0.x - o.x), ux = inv_d.d0 * (b0.w - o.x);
-            const float ly = inv_d.d1 * (b0.y - o.y), uy = inv_d.d1 * (b1.x - o.y);
-            const float lz = inv_d.d2 * (b0.z - o.z), uz = inv_d.d2 * (b1.y - o.z);
-            const float entry = fmaxf(fminf(lx, ux), fmaxf(fminf(ly, uy), fmaxf(fminf(lz, uz), 0.f)));
-            const float exit = fminf(fmaxf(lx, ux), fminf(fmaxf(ly, uy), fminf(fmaxf(lz, uz), t_max)));
-            if (entry <= exit && (seed_leaf < 0 || entry < seed_entry)) {
-                seed_leaf = __float_as_int(b1.z);
-                seed_entry = entry;
+
+    auto entered = [&](int32_t j, int32_t *leaf) {
+        const mb2::PVec4 b0 = boxes[2 * j], b1 = boxes[2 * j + 1];
+        const float lx = inv_d.d0 * (b0.x - o.x), ux = inv_d.d0 * (b0.w - o.x);
+        const float ly = inv_d.d1 * (b0.y - o.y), uy = inv_d.d1 * (b1.x - o.y);
+        const float lz = inv_d.d2 * (b0.z - o.z), uz = inv_d.d2 * (b1.y - o.z);
+        const float entry = fmaxf(fminf(lx, ux), fmaxf(fminf(ly, uy), fmaxf(fminf(lz, uz), 0.f)));
+        const float exit = fminf(fmaxf(lx, ux), fminf(fmaxf(ly, uy), fminf(fmaxf(lz, uz), t_max)));
+        *leaf = __float_as_int(b1.z);
+        return entry <= exit;
+    };
+
+    // (every peer runs the same number of chunk iterations: lanes of one warp may belong to
+    // worlds with different leaf counts)
+    for (int32_t base = 0; __any_sync(peers, base < num_boxes); base += 64) {
+        const int32_t left = num_boxes - base;
+        const int32_t chunk = left < 0 ? 0 : (left < 64 ? left : 64);
+        unsigned long long cand = 0;
+        for (int32_t j = 0; j < chunk; j++) {
+            int32_t leaf;
+            if (entered(base + j, &leaf)) cand |= 1ull << j;
+        }
+        while (__any_sync(peers, cand != 0)) {
+            int32_t leaf_idx = -1;
+            while (cand != 0) {
+                const int32_t j = __ffsll((long long)cand) - 1;
+                cand &= cand - 1;
+                int32_t leaf;
+                if (entered(base + j, &leaf)) {
+                    leaf_idx = leaf;
+                    break;
+                }
+            }
+            __syncwarp(peers);
+
+            if (leaf_idx >= 0) {
+                float hit_t;
+                math::Vector3 leaf_normal;
+                if (traceRayIntoLeaf(leaf_idx, o, d, 0.f, t_max, &hit_t, &leaf_normal)) {
+                    t_max = hit_t;
+                    closest = unpackEntity(s_.leafEntities[leaf_idx]);
+                    closest_normal = leaf_normal;
+                }
             }
         }
-        __syncwarp(peers);
-        if (seed_leaf >= 0) {
-            float hit_t;
-            math::Vector3 leaf_normal;
-            if (traceRayIntoLeaf(seed_leaf, o, d, 0.f, t_max, &hit_t, &leaf_normal)) {
-                t_max = hit_t;
-                closest = unpackEntity(s_.leafEntities[seed_leaf]);
-                closest_normal = leaf_normal;
-            }
-        }
-        __syncwarp(peers);
     }
+#else
+    // one-phase scan (the round-2 batch A mechanism), kept for A/B builds
+    const unsigned peers = __activemask();
+    const mb2::PVec4 *boxes = s_.orderedBoxes;
+    const int32_t num_boxes = s_.numTraversal;
     int32_t k = 0;
     bool walking = true;
+    Entity closest = Entity::none();
+    math::Vector3 closest_normal { 0, 0, 0 };
 
     while (__any_sync(peers, walking)) {
         int32_t leaf_idx = -1;
@@ -661,6 +692,7 @@ Entity BVH::traceRay(math::Vector3 o, math::Vector3 d, float *out_hit_t,
             }
         }
     }
+#endif
     if (closest == Entity::none()) return Entity::none();
     *out_hit_t = t_max;
     *out_hit_normal = closest_normal;
