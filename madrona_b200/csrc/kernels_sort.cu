@@ -177,6 +177,9 @@ constexpr uint32_t kValueMask = (1u << 30) - 1u;
 #define MB2_SORT_LOOK_WINDOW 8
 #endif
 constexpr int kLookWindow = MB2_SORT_LOOK_WINDOW;
+#ifndef MB2_SORT_MATCH_BALLOT
+#define MB2_SORT_MATCH_BALLOT 0
+#endif
 
 __global__ void __launch_bounds__(kSortThreads, 4)
 sortOnesweepKernel(SortParams p, int pass)
@@ -297,8 +300,23 @@ sortOnesweepKernel(SortParams p, int pass)
             key[r] = k;
             idx[r] = src;
             const uint32_t digit = (k >> shift) & 0xffu;
+#if MB2_SORT_MATCH_BALLOT
+            // lanes with the same digit by 8 + 1 ballots (full-rate VOTE) instead of one
+            // match.any (MIO pipe; its cost grows with the number of distinct values -- ~30 of
+            // 32 for random digits)
+            uint32_t same = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const bool bit = (digit >> b) & 1u;
+                const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+                same &= bit ? vote : ~vote;
+            }
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            peers_of[r] = valid ? (same & vmask) : (1u << lane);
+#else
             const uint32_t match_val = valid ? digit : (0x100u + (uint32_t)lane);
             peers_of[r] = __match_any_sync(0xffffffffu, match_val);
+#endif
         }
         // (b) stable ranks: the warp's running digit counts live in shared memory
 #pragma unroll
@@ -454,6 +472,14 @@ __device__ __forceinline__ void gatherTile(const void *src_v, void *dst_v, const
             dst[i] = a; dst[i + B] = b; dst[i + 2 * B] = c; dst[i + 3 * B] = d;
         }
         for (; i < total; i += B) dst[i] = at(i);
+    } else if (units_per_row == 3) {
+        // Vector3-sized rows (12 bytes as 3 x u32, 6 bytes as 3 x u16): constant divisor
+        auto at = [&](uint32_t k) { const uint32_t r = k / 3u; return src[(size_t)perm_s[r] * 3u + (k - r * 3u)]; };
+        for (; i + 3 * B < total; i += 4 * B) {
+            const UnitT a = at(i), b = at(i + B), c = at(i + 2 * B), d = at(i + 3 * B);
+            dst[i] = a; dst[i + B] = b; dst[i + 2 * B] = c; dst[i + 3 * B] = d;
+        }
+        for (; i < total; i += B) dst[i] = at(i);
     } else {
         for (; i < total; i += B) {
             const uint32_t r = i / units_per_row;
@@ -462,7 +488,7 @@ __device__ __forceinline__ void gatherTile(const void *src_v, void *dst_v, const
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 sortRearrangeKernel(SortParams p)
 {
     pdlSync();
@@ -476,11 +502,16 @@ sortRearrangeKernel(SortParams p)
     const int32_t num_cols = t.numColumns;
     const unsigned long long fused_mask = p.fuseCopyBack ? p.exportedMask : 0ull;
 
-    __shared__ __align__(128) int32_t perm_s[kRearrangeTile];
-    __shared__ __align__(8) unsigned long long perm_bar;
+    // two permutation buffers: the slice of the NEXT work item is in flight (TMA) while the
+    // current item gathers
+    __shared__ __align__(128) int32_t perm_buf[2][kRearrangeTile];
+    __shared__ __align__(8) unsigned long long perm_bar[2];
     __shared__ int32_t item_s;
-    if (threadIdx.x == 0) mbarInit(&perm_bar, 1);
-    uint32_t perm_phase = 0;
+    if (threadIdx.x == 0) {
+        mbarInit(&perm_bar[0], 1);
+        mbarInit(&perm_bar[1], 1);
+    }
+    uint32_t perm_phase[2] = { 0u, 0u };
 
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
@@ -508,26 +539,48 @@ sortRearrangeKernel(SortParams p)
     const int32_t chunks = (new_n + kRearrangeTile - 1) / kRearrangeTile;
     const int32_t num_phases = num_cols + __popcll(fused_mask & ((num_cols >= 64) ? ~0ull : ((1ull << num_cols) - 1ull)));
     const int64_t num_items = (int64_t)chunks * num_phases;
-    int32_t staged_chunk = -1;      // which slice of the permutation perm_s holds
-    while (true) {
-        __syncthreads();            // the previous item is done with perm_s / item_s
-        if (threadIdx.x == 0) item_s = atomicAdd(&p.ctrl->moveTicket, 1);
-        __syncthreads();
-        const int64_t item = item_s;
-        if (item >= num_items) break;
+    struct Item { int32_t col, chunk, row0, rows; bool copyBack, valid; };
+    auto decode = [&](const int64_t item) {
+        Item it { 0, 0, 0, 0, false, item < num_items };
+        if (!it.valid) return it;
         int32_t phase = (int32_t)(item / chunks);
-        const int32_t chunk = (int32_t)(item - (int64_t)phase * chunks);
+        it.chunk = (int32_t)(item - (int64_t)phase * chunks);
         // phase -> (column, gather | copy-back)
-        int32_t col = 0;
-        bool copy_back = false;
-        for (; col < num_cols; col++) {
-            const int32_t span = 1 + (int32_t)((fused_mask >> col) & 1ull);
-            if (phase < span) { copy_back = phase == 1; break; }
+        for (; it.col < num_cols; it.col++) {
+            const int32_t span = 1 + (int32_t)((fused_mask >> it.col) & 1ull);
+            if (phase < span) { it.copyBack = phase == 1; break; }
             phase -= span;
         }
-        const int32_t row0 = chunk * kRearrangeTile;
-        const int32_t rows = min(kRearrangeTile, new_n - row0);
+        it.row0 = it.chunk * kRearrangeTile;
+        it.rows = min(kRearrangeTile, new_n - it.row0);
+        return it;
+    };
+    // take the next ticket; a gather item over a whole chunk gets its slice of the permutation
+    // requested right away into buffer `buf`
+    auto fetch = [&](const int buf) {
+        __syncthreads();            // everybody is done with item_s and with perm_buf[buf]
+        if (threadIdx.x == 0) item_s = atomicAdd(&p.ctrl->moveTicket, 1);
+        __syncthreads();
+        const Item it = decode(item_s);
+        if (it.valid && !it.copyBack && it.rows == kRearrangeTile && threadIdx.x == 0) {
+            fenceProxyAsync();      // a partial chunk may have written this buffer with plain stores
+            mbarExpectTx(&perm_bar[buf], kRearrangeTile * 4);
+            tmaLoad1D(perm_buf[buf], perm + it.row0, kRearrangeTile * 4, &perm_bar[buf]);
+        }
+        return it;
+    };
+
+    int buf = 0;
+    Item next = fetch(buf);
+    while (next.valid) {
+        const Item cur = next;
+        const int cur_buf = buf;
+        buf ^= 1;
+        next = fetch(buf);          // overlaps with the gathers below
+        const int32_t col = cur.col, row0 = cur.row0, rows = cur.rows;
+        const bool copy_back = cur.copyBack;
         const uint32_t bytes = t.columnBytes[col];
+        int32_t *perm_s = perm_buf[cur_buf];
 
         if (copy_back) {
             // every gather chunk of this column has landed in the twin
@@ -553,21 +606,12 @@ sortRearrangeKernel(SortParams p)
             continue;
         }
 
-        if (staged_chunk != chunk) {
-            if (rows == kRearrangeTile) {
-                // the chunk's slice of the permutation: one bulk copy
-                if (threadIdx.x == 0) {
-                    fenceProxyAsync();
-                    mbarExpectTx(&perm_bar, kRearrangeTile * 4);
-                    tmaLoad1D(perm_s, perm + row0, kRearrangeTile * 4, &perm_bar);
-                }
-                mbarWait(&perm_bar, perm_phase);
-                perm_phase ^= 1u;
-            } else {
-                for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
-                __syncthreads();
-            }
-            staged_chunk = chunk;
+        if (rows == kRearrangeTile) {
+            mbarWait(&perm_bar[cur_buf], perm_phase[cur_buf]);
+            perm_phase[cur_buf] ^= 1u;
+        } else {
+            for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
+            __syncthreads();
         }
 
         const void *src = t.columns[col];
@@ -877,7 +921,7 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
     const int rtiles = (t.capacity + kRearrangeTile - 1) / kRearrangeTile;
     static const int move_per_sm = [] {
         const char *v = getenv("MADRONA_B200_REARRANGE_BLOCKS_PER_SM");
-        return (v && *v) ? std::max(1, atoi(v)) : 8;
+        return (v && *v) ? std::max(1, atoi(v)) : 6;    // == the kernel's resident blocks per SM
     }();
     const int rblocks = std::max(1, std::min(rtiles * std::max(1, t.numColumns / 2), ex->numSMs * move_per_sm));
     launchK(sortRearrangeKernel, dim3(rblocks), dim3(256), 0, s, p);
