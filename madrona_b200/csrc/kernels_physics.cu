@@ -603,7 +603,7 @@ __device__ __forceinline__ void forEachPartner(const WorldBVH &bvh, const PairVi
 constexpr int kMaxStagedLeaves = 128;          // bodies per world the candidate search handles
 constexpr int kLeafMaskWords = kMaxStagedLeaves / 64;
 
-struct StagedLeaf {
+struct __align__(16) StagedLeaf {
     float box[6];       // the leaf's slot in its parent node (grow-only since the last rebuild)
     i32 entityID;
     u32 arch;
