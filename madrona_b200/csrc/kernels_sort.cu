@@ -177,9 +177,6 @@ constexpr uint32_t kValueMask = (1u << 30) - 1u;
 #define MB2_SORT_LOOK_WINDOW 8
 #endif
 constexpr int kLookWindow = MB2_SORT_LOOK_WINDOW;
-#ifndef MB2_SORT_MATCH_BALLOT
-#define MB2_SORT_MATCH_BALLOT 0
-#endif
 
 __global__ void __launch_bounds__(kSortThreads, 4)
 sortOnesweepKernel(SortParams p, int pass)
@@ -275,9 +272,9 @@ sortOnesweepKernel(SortParams p, int pass)
             mbarWait(&tile_bar, tile_phase);
             tile_phase ^= 1u;
         }
-        // (a) load the items and match digits across the warp: kItemsPerThread INDEPENDENT
-        //     match.any operations in flight (its latency was 17 % of the pass's stall samples
-        //     when each match sat between the shared-memory updates of (b))
+        // (a) load the items and match digits across the warp: kItemsPerThread independent
+        //     match.any operations in flight instead of one between each pair of shared-memory
+        //     updates of (b)
         uint32_t peers_of[kItemsPerThread];
 #pragma unroll
         for (int r = 0; r < kItemsPerThread; r++) {
@@ -300,23 +297,8 @@ sortOnesweepKernel(SortParams p, int pass)
             key[r] = k;
             idx[r] = src;
             const uint32_t digit = (k >> shift) & 0xffu;
-#if MB2_SORT_MATCH_BALLOT
-            // lanes with the same digit by 8 + 1 ballots (full-rate VOTE) instead of one
-            // match.any (MIO pipe; its cost grows with the number of distinct values -- ~30 of
-            // 32 for random digits)
-            uint32_t same = 0xffffffffu;
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                const bool bit = (digit >> b) & 1u;
-                const uint32_t vote = __ballot_sync(0xffffffffu, bit);
-                same &= bit ? vote : ~vote;
-            }
-            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-            peers_of[r] = valid ? (same & vmask) : (1u << lane);
-#else
             const uint32_t match_val = valid ? digit : (0x100u + (uint32_t)lane);
             peers_of[r] = __match_any_sync(0xffffffffu, match_val);
-#endif
         }
         // (b) stable ranks: the warp's running digit counts live in shared memory
 #pragma unroll
@@ -472,14 +454,6 @@ __device__ __forceinline__ void gatherTile(const void *src_v, void *dst_v, const
             dst[i] = a; dst[i + B] = b; dst[i + 2 * B] = c; dst[i + 3 * B] = d;
         }
         for (; i < total; i += B) dst[i] = at(i);
-    } else if (units_per_row == 3) {
-        // Vector3-sized rows (12 bytes as 3 x u32, 6 bytes as 3 x u16): constant divisor
-        auto at = [&](uint32_t k) { const uint32_t r = k / 3u; return src[(size_t)perm_s[r] * 3u + (k - r * 3u)]; };
-        for (; i + 3 * B < total; i += 4 * B) {
-            const UnitT a = at(i), b = at(i + B), c = at(i + 2 * B), d = at(i + 3 * B);
-            dst[i] = a; dst[i + B] = b; dst[i + 2 * B] = c; dst[i + 3 * B] = d;
-        }
-        for (; i < total; i += B) dst[i] = at(i);
     } else {
         for (; i < total; i += B) {
             const uint32_t r = i / units_per_row;
@@ -488,7 +462,7 @@ __device__ __forceinline__ void gatherTile(const void *src_v, void *dst_v, const
     }
 }
 
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256)
 sortRearrangeKernel(SortParams p)
 {
     pdlSync();
@@ -502,16 +476,11 @@ sortRearrangeKernel(SortParams p)
     const int32_t num_cols = t.numColumns;
     const unsigned long long fused_mask = p.fuseCopyBack ? p.exportedMask : 0ull;
 
-    // two permutation buffers: the slice of the NEXT work item is in flight (TMA) while the
-    // current item gathers
-    __shared__ __align__(128) int32_t perm_buf[2][kRearrangeTile];
-    __shared__ __align__(8) unsigned long long perm_bar[2];
+    __shared__ __align__(128) int32_t perm_s[kRearrangeTile];
+    __shared__ __align__(8) unsigned long long perm_bar;
     __shared__ int32_t item_s;
-    if (threadIdx.x == 0) {
-        mbarInit(&perm_bar[0], 1);
-        mbarInit(&perm_bar[1], 1);
-    }
-    uint32_t perm_phase[2] = { 0u, 0u };
+    if (threadIdx.x == 0) mbarInit(&perm_bar, 1);
+    uint32_t perm_phase = 0;
 
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
@@ -539,48 +508,26 @@ sortRearrangeKernel(SortParams p)
     const int32_t chunks = (new_n + kRearrangeTile - 1) / kRearrangeTile;
     const int32_t num_phases = num_cols + __popcll(fused_mask & ((num_cols >= 64) ? ~0ull : ((1ull << num_cols) - 1ull)));
     const int64_t num_items = (int64_t)chunks * num_phases;
-    struct Item { int32_t col, chunk, row0, rows; bool copyBack, valid; };
-    auto decode = [&](const int64_t item) {
-        Item it { 0, 0, 0, 0, false, item < num_items };
-        if (!it.valid) return it;
-        int32_t phase = (int32_t)(item / chunks);
-        it.chunk = (int32_t)(item - (int64_t)phase * chunks);
-        // phase -> (column, gather | copy-back)
-        for (; it.col < num_cols; it.col++) {
-            const int32_t span = 1 + (int32_t)((fused_mask >> it.col) & 1ull);
-            if (phase < span) { it.copyBack = phase == 1; break; }
-            phase -= span;
-        }
-        it.row0 = it.chunk * kRearrangeTile;
-        it.rows = min(kRearrangeTile, new_n - it.row0);
-        return it;
-    };
-    // take the next ticket; a gather item over a whole chunk gets its slice of the permutation
-    // requested right away into buffer `buf`
-    auto fetch = [&](const int buf) {
-        __syncthreads();            // everybody is done with item_s and with perm_buf[buf]
+    int32_t staged_chunk = -1;      // which slice of the permutation perm_s holds
+    while (true) {
+        __syncthreads();            // the previous item is done with perm_s / item_s
         if (threadIdx.x == 0) item_s = atomicAdd(&p.ctrl->moveTicket, 1);
         __syncthreads();
-        const Item it = decode(item_s);
-        if (it.valid && !it.copyBack && it.rows == kRearrangeTile && threadIdx.x == 0) {
-            fenceProxyAsync();      // a partial chunk may have written this buffer with plain stores
-            mbarExpectTx(&perm_bar[buf], kRearrangeTile * 4);
-            tmaLoad1D(perm_buf[buf], perm + it.row0, kRearrangeTile * 4, &perm_bar[buf]);
+        const int64_t item = item_s;
+        if (item >= num_items) break;
+        int32_t phase = (int32_t)(item / chunks);
+        const int32_t chunk = (int32_t)(item - (int64_t)phase * chunks);
+        // phase -> (column, gather | copy-back)
+        int32_t col = 0;
+        bool copy_back = false;
+        for (; col < num_cols; col++) {
+            const int32_t span = 1 + (int32_t)((fused_mask >> col) & 1ull);
+            if (phase < span) { copy_back = phase == 1; break; }
+            phase -= span;
         }
-        return it;
-    };
-
-    int buf = 0;
-    Item next = fetch(buf);
-    while (next.valid) {
-        const Item cur = next;
-        const int cur_buf = buf;
-        buf ^= 1;
-        next = fetch(buf);          // overlaps with the gathers below
-        const int32_t col = cur.col, row0 = cur.row0, rows = cur.rows;
-        const bool copy_back = cur.copyBack;
+        const int32_t row0 = chunk * kRearrangeTile;
+        const int32_t rows = min(kRearrangeTile, new_n - row0);
         const uint32_t bytes = t.columnBytes[col];
-        int32_t *perm_s = perm_buf[cur_buf];
 
         if (copy_back) {
             // every gather chunk of this column has landed in the twin
@@ -606,12 +553,21 @@ sortRearrangeKernel(SortParams p)
             continue;
         }
 
-        if (rows == kRearrangeTile) {
-            mbarWait(&perm_bar[cur_buf], perm_phase[cur_buf]);
-            perm_phase[cur_buf] ^= 1u;
-        } else {
-            for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
-            __syncthreads();
+        if (staged_chunk != chunk) {
+            if (rows == kRearrangeTile) {
+                // the chunk's slice of the permutation: one bulk copy
+                if (threadIdx.x == 0) {
+                    fenceProxyAsync();
+                    mbarExpectTx(&perm_bar, kRearrangeTile * 4);
+                    tmaLoad1D(perm_s, perm + row0, kRearrangeTile * 4, &perm_bar);
+                }
+                mbarWait(&perm_bar, perm_phase);
+                perm_phase ^= 1u;
+            } else {
+                for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) perm_s[i] = perm[row0 + i];
+                __syncthreads();
+            }
+            staged_chunk = chunk;
         }
 
         const void *src = t.columns[col];
@@ -622,35 +578,15 @@ sortRearrangeKernel(SortParams p)
             const unsigned long long *sp = (const unsigned long long *)src;
             unsigned long long *dp = (unsigned long long *)dst;
             EntitySlot *slots = p.state->entitySlots;
-            const int32_t my_cap = p.state->entityCapacity;
-            auto repoint = [&](const unsigned long long e, const EntitySlot &s, const int32_t row) {
-                const uint32_t gen = (uint32_t)(e & 0xFFFFFFFFull);
-                const int32_t id = (int32_t)(uint32_t)(e >> 32);
-                if (id >= 0 && gen != 0xFFFFFFFFu && id < my_cap && s.gen == gen && s.a == (int32_t)p.archetype) {
-                    slots[id].b = row;
-                }
-            };
-            auto slotOf = [&](const unsigned long long e) {
-                // ids outside the store read slot 0 (the check in repoint() rejects them)
-                const int32_t id = (int32_t)(uint32_t)(e >> 32);
-                return slots[(id >= 0 && id < my_cap) ? id : 0];
-            };
-            const int32_t B = (int32_t)blockDim.x;
-            int32_t i = (int32_t)threadIdx.x;
-            // four independent gather -> slot-check chains per thread (the random 12-byte slot
-            // reads were a third of this kernel's stall samples one element at a time)
-            for (; i + 3 * B < rows; i += 4 * B) {
-                const unsigned long long e0 = sp[perm_s[i]], e1 = sp[perm_s[i + B]];
-                const unsigned long long e2 = sp[perm_s[i + 2 * B]], e3 = sp[perm_s[i + 3 * B]];
-                const EntitySlot s0 = slotOf(e0), s1 = slotOf(e1), s2 = slotOf(e2), s3 = slotOf(e3);
-                dp[row0 + i] = e0; dp[row0 + i + B] = e1; dp[row0 + i + 2 * B] = e2; dp[row0 + i + 3 * B] = e3;
-                repoint(e0, s0, row0 + i); repoint(e1, s1, row0 + i + B);
-                repoint(e2, s2, row0 + i + 2 * B); repoint(e3, s3, row0 + i + 3 * B);
-            }
-            for (; i < rows; i += B) {
+            for (int32_t i = threadIdx.x; i < rows; i += blockDim.x) {
                 const unsigned long long e = sp[perm_s[i]];
                 dp[row0 + i] = e;
-                repoint(e, slotOf(e), row0 + i);
+                const uint32_t gen = (uint32_t)(e & 0xFFFFFFFFull);
+                const int32_t id = (int32_t)(uint32_t)(e >> 32);
+                if (id >= 0 && gen != 0xFFFFFFFFu && id < p.state->entityCapacity &&
+                        slots[id].gen == gen && slots[id].a == (int32_t)p.archetype) {
+                    slots[id].b = row0 + i;
+                }
             }
         } else if ((bytes & 15u) == 0) {
             gatherTile<uint4>(src, dst, perm_s, row0, rows, bytes >> 4);
@@ -900,7 +836,8 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
     p.exportedMask = mask;
     static const int fuse_copy_back = [] {
         const char *v = getenv("MADRONA_B200_SORT_FUSE_COPYBACK");
-        // B200, sortcheck 3.1M rows: fused 0.458 ms/step, separate copy-back launch 0.442
+        // B200, sortcheck 3.1M rows, one box: copy-back items fused into the rearrange kernel
+        // 0.458 ms/step, separate copy-back launch 0.442 -> separate by default
         return (v && *v) ? atoi(v) : 0;
     }();
     p.fuseCopyBack = fuse_copy_back && mask ? 1 : 0;
@@ -921,7 +858,7 @@ void launchSortArchetype(Executor *ex, uint32_t archetype, int32_t col, cudaStre
     const int rtiles = (t.capacity + kRearrangeTile - 1) / kRearrangeTile;
     static const int move_per_sm = [] {
         const char *v = getenv("MADRONA_B200_REARRANGE_BLOCKS_PER_SM");
-        return (v && *v) ? std::max(1, atoi(v)) : 6;    // == the kernel's resident blocks per SM
+        return (v && *v) ? std::max(1, atoi(v)) : 8;
     }();
     const int rblocks = std::max(1, std::min(rtiles * std::max(1, t.numColumns / 2), ex->numSMs * move_per_sm));
     launchK(sortRearrangeKernel, dim3(rblocks), dim3(256), 0, s, p);
