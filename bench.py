@@ -146,15 +146,20 @@ def make_actions(desc, sim, W, steps, seed):
 
 # what actually bounds the dominant kernel (ncu summaries under profiles/); the JSON
 # contract only knows "hbm" / "tensor", so the HBM fraction is always reported
-_LATENCY = ("per-world kernel: instruction-issue / latency bound (ncu: 29-53 % issue utilisation, "
-            "16-24 warps/SM), as SURVEY 8d anticipated; the HBM fraction is reported for completeness")
+_LATENCY = ("per-world / per-candidate kernel: one wave whose duration is the slowest world's dependent chain; "
+            "instruction-issue / latency bound (ncu round 2, profiles/r2c_ncu_summary.txt: 19-43 % issue "
+            "utilisation, 18-35 % achieved occupancy), as SURVEY 8d anticipated; the HBM fraction is reported "
+            "for completeness")
 ROOFLINE_NOTES = {
     "phys_narrowphase": _LATENCY, "phys_solve_positions": _LATENCY, "phys_solve_velocities": _LATENCY,
     "phys_find_candidates": _LATENCY,
-    "raycast": "instruction bound (ncu: 59 % issue utilisation); algorithmic bytes = the 8 B written per pixel",
-    "sort_archetype": "whole sort (histogram + P onesweep passes + fused rearrange + copy-back); random "
-                      "row permutations fetch a 32-byte sector per 4-16-byte element",
-    "compact_archetype": "whole compaction sort (histogram + P onesweep passes + fused rearrange + copy-back)",
+    "raycast": "instruction bound (ncu: 71 % issue utilisation, 30 active threads per instruction); algorithmic "
+               "bytes = the 8 B written per pixel",
+    "sort_archetype": "whole sort (histogram + P onesweep passes + column-major gather + copy-back); a random "
+                      "row permutation makes the gather and the entity re-pointing latency bound (ncu: 58 % "
+                      "long-scoreboard stalls), each onesweep pass is bound by its per-tile serial phases "
+                      "(DESIGN.md 3.1)",
+    "compact_archetype": "whole compaction sort (histogram + P onesweep passes + column-major gather + copy-back)",
 }
 
 
