@@ -12,14 +12,18 @@
 // with a device-wide barrier between each and moves every column twice with
 // per-element memcpy):
 //   1 histogram kernel  (all passes' digit histograms in one read of the keys)
-//   P onesweep kernels  (decoupled look-back, ticketed persistent tiles,
+//   P onesweep kernels  (TMA-staged tiles, decoupled look-back that reads 8
+//                        predecessors per step, ticketed persistent tiles,
 //                        warp match-any ranking -> stable)
-//   1 rearrange kernel  (ALL columns in one launch, each column read once and
+//   1 rearrange kernel  (ALL columns in one launch as ticketed (column, chunk)
+//                        items in column-major order, each column read once and
 //                        written once into its twin buffer; the table's column
 //                        pointers are flipped on the device, so no copy-back;
 //                        also entity remap + offsets/counts + scratch reset)
 // => P+2 launches per sort.  Exported columns must keep their address, so
-// they (only) get one extra copy-back launch.
+// they (only) get one extra copy-back launch (or, behind
+// MADRONA_B200_SORT_FUSE_COPYBACK=1, copy-back items inside the rearrange
+// kernel -- measured slower on B200).
 #include "engine.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -417,7 +421,7 @@ sortOnesweepKernel(SortParams p, int pass)
 // in its widest aligned unit (16/8/4/1 bytes) with coalesced stores, four independent
 // gathers in flight per thread.
 //
-// Exported columns must keep their address.  With fuseCopyBack their copy-back items
+// Exported columns must keep their address.  With fuseCopyBack (off by default) their copy-back items
 // (twin -> exported address, 16-byte units) follow the column's gather items in ticket
 // order and wait on the column's chunk counter, so the twin is re-read while it is still
 // in L2 and no extra launch is needed.  Deadlock free for any grid size: a copy-back item
