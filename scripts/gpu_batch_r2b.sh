@@ -1,6 +1,10 @@
 #!/bin/bash
 # Round-2 batch B (one gpurun call): parity of the new kernels, bench lines, one-box A/Bs of
 # every switch added since batch A, then ncu captures (last: a killed ncu can wedge a GPU).
+# Variant libraries used below were built beforehand (git-ignored) with
+#   scripts/build_variants.sh bodyold "-DMB2_BODY_MINB=1" look1 "-DMB2_SORT_LOOK_WINDOW=1" sort12 "-DMB2_SORT_ITEMS=12" \
+#       sort16 "-DMB2_SORT_ITEMS=16" rc2 "-DMB2_RAYCAST_MINB=2"
+# at commit 0b970f5 (the defaults of that commit: fused copy-back ON, 32-register row kernels, traceRay seed ON).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T0=$(date +%s)

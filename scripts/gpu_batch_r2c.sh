@@ -2,6 +2,8 @@
 # Round-2 batch C (one gpurun call): parity, one-box A/Bs of the last switches (traceRay candidate
 # mask, ballot digit matching, rearrange residency), then the bench lines and ncu captures of the
 # configuration the A/Bs select (recorded in gpurun_out/r2c_selected.env), ncu last.
+# The ballot variant was built beforehand (git-ignored) with
+#   scripts/build_variants.sh ballot "-DMB2_SORT_MATCH_BALLOT=1"      (commit c1ae823; that code path was removed afterwards)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T0=$(date +%s)
